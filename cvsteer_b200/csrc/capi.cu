@@ -1,0 +1,680 @@
+// C ABI of libcvsteer_b200.so (include/cvsteer_c.h).  Host-side state lives here: tap tables, the resident
+// class state of a set-up image, streams, staging.  All arithmetic on pixels happens in CUDA kernels; there
+// is no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/cvsteer_c.h"
+#include "launch.h"
+#include "taps.h"
+
+using namespace cvs;
+
+#define MARCH_MAX_OUT_HOST 32
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU_TRY(expr)                                                                                         \
+    do {                                                                                                     \
+        cudaError_t e__ = (expr);                                                                            \
+        if (e__ != cudaSuccess) return fail(CVS_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char* cvs_version(void) { return "cvsteer_b200 0.1.0 (sm_100a)"; }
+extern "C" const char* cvs_last_error(void) { return g_err; }
+
+extern "C" int cvs_device_count(int* count)
+{
+    if (!count) return fail(CVS_ERR_INVALID_ARG, "count is null");
+    CU_TRY(cudaGetDeviceCount(count));
+    return CVS_OK;
+}
+
+extern "C" int cvs_g2_make_taps(int which, int width, float spacing, float* dst)
+{
+    if (which < 0 || which >= G2_NUM_TAPSETS || width < 1 || width > MAX_WIDTH || !dst)
+        return fail(CVS_ERR_INVALID_ARG, "cvs_g2_make_taps: which=%d width=%d", which, width);
+    make_taps_g2(which, width, spacing, dst);
+    return CVS_OK;
+}
+
+extern "C" int cvs_g4_make_taps(int which, int width, float spacing, float* dst)
+{
+    if (which < 0 || which >= G4_NUM_TAPSETS || width < 1 || width > MAX_WIDTH || !dst)
+        return fail(CVS_ERR_INVALID_ARG, "cvs_g4_make_taps: which=%d width=%d", which, width);
+    make_taps_g4(which, width, spacing, dst);
+    return CVS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= bytes) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e == cudaSuccess) bytes = n;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Filter {
+    int family;  // 2 or 4
+    int device;
+    FamilyTaps taps;
+    cudaStream_t stream = nullptr;
+    // resident class state of the last setup()
+    int rows = 0, cols = 0;
+    size_t pitch = 0;         // bytes, multiple of 128 (TMA needs 16)
+    DevBuf in, state, work, scratch;
+    int nstate = 0;           // planes in `state`: G2 12 (7 basis, c1..c3, theta, strength); G4 11
+    bool ready = false;
+    LaunchInfo last{};
+
+    float* state_plane(int i) const { return reinterpret_cast<float*>(static_cast<char*>(state.p) + (size_t)i * pitch * rows); }
+    float* work_plane(int i) const { return reinterpret_cast<float*>(static_cast<char*>(work.p) + (size_t)i * pitch * rows); }
+};
+
+int filter_create(Filter** out, int family, int device, int width, float spacing)
+{
+    if (!out) return fail(CVS_ERR_INVALID_ARG, "out is null");
+    *out = nullptr;
+    if (width < 1 || width > MAX_WIDTH) return fail(CVS_ERR_INVALID_ARG, "width %d outside [1, %d]", width, (int)MAX_WIDTH);
+    int ndev = 0;
+    CU_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(CVS_ERR_INVALID_ARG, "device %d of %d", device, ndev);
+    Filter* f = new (std::nothrow) Filter();
+    if (!f) return fail(CVS_ERR_CUDA, "out of host memory");
+    f->family = family;
+    f->device = device;
+    f->taps.width = width;
+    f->taps.nsets = family == 2 ? (int)G2_NUM_TAPSETS : (int)G4_NUM_TAPSETS;
+    memset(f->taps.t, 0, sizeof(f->taps.t));
+    for (int s = 0; s < f->taps.nsets; ++s) {
+        if (family == 2) make_taps_g2(s, width, spacing, f->taps.t[s]);
+        else make_taps_g4(s, width, spacing, f->taps.t[s]);
+    }
+    f->nstate = family == 2 ? 12 : 11;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete f;
+        return fail(CVS_ERR_CUDA, "stream create: %s", cudaGetErrorString(e));
+    }
+    *out = f;
+    return CVS_OK;
+}
+
+int filter_destroy(Filter* f)
+{
+    if (!f) return CVS_OK;
+    cudaSetDevice(f->device);
+    if (f->stream) {
+        cudaStreamSynchronize(f->stream);
+        cudaStreamDestroy(f->stream);
+    }
+    f->in.release();
+    f->state.release();
+    f->work.release();
+    f->scratch.release();
+    delete f;
+    return CVS_OK;
+}
+
+BatchGeom whole_frame_geom(const void* in, bool u8, int n, int rows, int cols, size_t in_pitch, size_t in_fs, size_t out_pitch,
+                           size_t out_fs)
+{
+    BatchGeom g{};
+    g.in = in;
+    g.in_u8 = u8;
+    g.n = n;
+    g.cols = cols;
+    g.buf_rows = rows;
+    g.full_rows = rows;
+    g.y_origin = 0;
+    g.out_row_begin = 0;
+    g.out_row_end = rows;
+    g.out_row_origin = 0;
+    g.in_pitch = in_pitch;
+    g.in_frame_stride = in_fs;
+    g.out_pitch = out_pitch;
+    g.out_frame_stride = out_fs;
+    return g;
+}
+
+int geom_from_batch(const cvs_batch* b, BatchGeom* g)
+{
+    if (!b || !b->in) return fail(CVS_ERR_INVALID_ARG, "batch or batch->in is null");
+    if (b->n <= 0 || b->rows <= 0 || b->cols <= 0) return fail(CVS_ERR_INVALID_ARG, "batch n/rows/cols must be positive");
+    const size_t esz = b->in_is_u8 ? 1 : 4;
+    if (b->in_pitch < (size_t)b->cols * esz) return fail(CVS_ERR_INVALID_ARG, "in_pitch %zu < cols*%zu", b->in_pitch, esz);
+    if (b->out_pitch < (size_t)b->cols * 4 / 2) return fail(CVS_ERR_INVALID_ARG, "out_pitch too small");
+    *g = whole_frame_geom(b->in, b->in_is_u8 != 0, b->n, b->rows, b->cols, b->in_pitch, b->in_frame_stride, b->out_pitch,
+                          b->out_frame_stride);
+    if (b->full_rows > 0) {
+        g->full_rows = b->full_rows;
+        g->y_origin = b->y_origin;
+        g->out_row_begin = b->out_row_begin;
+        g->out_row_end = b->out_row_end;
+        g->out_row_origin = b->out_row_origin;
+        if (g->y_origin < 0 || g->y_origin + g->buf_rows > g->full_rows)
+            return fail(CVS_ERR_INVALID_ARG, "band buffer rows [%d,%d) outside image of %d rows", g->y_origin, g->y_origin + g->buf_rows,
+                        g->full_rows);
+    }
+    return CVS_OK;
+}
+
+// The band contract for a filter of radius R: the buffer must hold image rows [out_row_begin-R, out_row_end+R) clipped to
+// the image.
+int check_band(const BatchGeom& g, int radius, int full_rows_out_level)
+{
+    if (g.out_row_begin < 0 || g.out_row_end > full_rows_out_level || g.out_row_begin >= g.out_row_end)
+        return fail(CVS_ERR_INVALID_ARG, "output rows [%d,%d) invalid", g.out_row_begin, g.out_row_end);
+    (void)radius;
+    return CVS_OK;
+}
+
+int run_fused(Filter* f, const BatchGeom& g, unsigned mask, const SteerSpec& st, float* const* outs, cudaStream_t stream)
+{
+    CU_TRY(cudaSetDevice(f->device));
+    float* scratch = nullptr;
+    if (!uses_march_path(f->family, f->taps.width)) {
+        CU_TRY(f->scratch.reserve(scratch_bytes_generic(f->family, g)));
+        scratch = static_cast<float*>(f->scratch.p);
+    }
+    CU_TRY(launch_basis_fused(f->family, f->taps, g, mask, st, outs, scratch, stream, &f->last));
+    return CVS_OK;
+}
+
+int filter_setup(Filter* f, const void* image, bool u8, int rows, int cols, size_t step)
+{
+    if (!f) return fail(CVS_ERR_INVALID_ARG, "handle is null");
+    if (!image || rows <= 0 || cols <= 0) return fail(CVS_ERR_INVALID_ARG, "empty image (%p, %dx%d)", image, rows, cols);
+    const size_t esz = u8 ? 1 : 4;
+    if (step < (size_t)cols * esz) return fail(CVS_ERR_INVALID_ARG, "step %zu < cols*%zu", step, esz);
+    CU_TRY(cudaSetDevice(f->device));
+    f->ready = false;
+    f->rows = rows;
+    f->cols = cols;
+    f->pitch = align_up((size_t)cols * 4, 128);
+    const size_t in_pitch = u8 ? align_up((size_t)cols, 128) : f->pitch;
+    CU_TRY(f->in.reserve(in_pitch * rows));
+    CU_TRY(f->state.reserve(f->pitch * rows * (size_t)f->nstate));
+    CU_TRY(cudaMemcpy2DAsync(f->in.p, in_pitch, image, step, (size_t)cols * esz, rows, cudaMemcpyHostToDevice, f->stream));
+    BatchGeom g = whole_frame_geom(f->in.p, u8, 1, rows, cols, in_pitch, in_pitch * rows, f->pitch, f->pitch * rows);
+    float* outs[MAX_TAPS] = {nullptr};
+    for (int i = 0; i < f->nstate; ++i) outs[i] = f->state_plane(i);
+    SteerSpec st{};
+    st.source = CVS_STEER_DOMINANT;
+    const unsigned mask = f->family == 2 ? CVS_G2_MASK_STATE : CVS_G4_MASK_BASIS;
+    int rc = run_fused(f, g, mask, st, outs, f->stream);
+    if (rc) return rc;
+    CU_TRY(cudaStreamSynchronize(f->stream));  // the caller may free `image` as soon as setup() returns
+    f->ready = true;
+    return CVS_OK;
+}
+
+int download(Filter* f, const float* dplane, float* dst, size_t step)
+{
+    if (!dst) return CVS_OK;
+    if (step < (size_t)f->cols * 4) return fail(CVS_ERR_INVALID_ARG, "dst step %zu < cols*4", step);
+    CU_TRY(cudaMemcpy2DAsync(dst, step, dplane, f->pitch, (size_t)f->cols * 4, f->rows, cudaMemcpyDeviceToHost, f->stream));
+    return CVS_OK;
+}
+
+int filter_get_plane(Filter* f, int plane, float* dst, size_t step)
+{
+    if (!f || !dst) return fail(CVS_ERR_INVALID_ARG, "null argument");
+    if (!f->ready) return fail(CVS_ERR_NOT_SETUP, "get_plane before setup");
+    if (plane < 0 || plane >= f->nstate) return fail(CVS_ERR_INVALID_ARG, "plane %d not part of the class state", plane);
+    CU_TRY(cudaSetDevice(f->device));
+    int rc = download(f, f->state_plane(plane), dst, step);
+    if (rc) return rc;
+    CU_TRY(cudaStreamSynchronize(f->stream));
+    return CVS_OK;
+}
+
+// steer on the stored planes.  outs_host indexed by family plane id; theta host map optional.
+int filter_steer(Filter* f, int source, float theta, const float* theta_host, size_t theta_step, unsigned mask, float* const* outs_host,
+                 size_t step)
+{
+    if (!f) return fail(CVS_ERR_INVALID_ARG, "handle is null");
+    if (!f->ready) return fail(CVS_ERR_NOT_SETUP, "steer before setup");
+    CU_TRY(cudaSetDevice(f->device));
+    const int nplanes = f->family == 2 ? (int)CVS_G2_NPLANES : (int)CVS_G4_NPLANES;
+    const size_t plane_bytes = f->pitch * f->rows;
+    CU_TRY(f->work.reserve(plane_bytes * 6));  // 5 outputs + an uploaded theta map
+    SteerSpec st{};
+    st.source = source;
+    float c2t = 0.f, s2t = 0.f;
+    size_t th_pitch = f->pitch;
+    if (source == CVS_STEER_SCALAR) {
+        // the reference evaluates std::cos/std::sin on the float angle on the host (G2.cpp:140, G4.cpp:116) and
+        // cos/sin of (theta * 2.0) in double (G2.cpp:163)
+        st.cos_t = std::cos(theta);
+        st.sin_t = std::sin(theta);
+        c2t = (float)std::cos(theta * 2.0);
+        s2t = (float)std::sin(theta * 2.0);
+    } else if (theta_host) {
+        if (theta_step < (size_t)f->cols * 4) return fail(CVS_ERR_SIZE_MISMATCH, "theta step %zu < cols*4", theta_step);
+        CU_TRY(cudaMemcpy2DAsync(f->work_plane(5), f->pitch, theta_host, theta_step, (size_t)f->cols * 4, f->rows, cudaMemcpyHostToDevice,
+                                 f->stream));
+        st.theta_map = f->work_plane(5);
+    } else {
+        if (f->family != 2) return fail(CVS_ERR_INVALID_ARG, "G4 has no dominant-orientation map (reference: G4.h:40-41 never assigned)");
+        st.theta_map = f->state_plane(CVS_THETA);  // steer(getDominantOrientationAngle(), ...) without a host round trip
+    }
+    float* outs_dev[MARCH_MAX_OUT_HOST] = {nullptr};
+    int slot = 0;
+    for (int p = 0; p < nplanes; ++p)
+        if (mask >> p & 1u) outs_dev[p] = f->work_plane(slot++);
+    if (slot > 5) return fail(CVS_ERR_INVALID_ARG, "too many steer outputs");
+    PlaneSet ps{};
+    for (int i = 0; i < f->nstate && i < 16; ++i) ps.p[i] = f->state_plane(i);
+    ps.pitch = f->pitch;
+    if (f->family == 2)
+        CU_TRY(launch_g2_steer_planes(ps, f->rows, f->cols, st, c2t, s2t, th_pitch, mask, outs_dev, f->pitch, f->stream));
+    else
+        CU_TRY(launch_g4_steer_planes(ps, f->rows, f->cols, st, th_pitch, mask, outs_dev, f->pitch, f->stream));
+    for (int p = 0; p < nplanes; ++p)
+        if (mask >> p & 1u) {
+            int rc = download(f, outs_dev[p], outs_host[p], step);
+            if (rc) return rc;
+        }
+    CU_TRY(cudaStreamSynchronize(f->stream));
+    return CVS_OK;
+}
+
+}  // namespace
+
+// cvs_g2 / cvs_g4 are opaque to callers; both are a Filter underneath.
+
+// ================================ G2 ================================
+extern "C" int cvs_g2_create(cvs_g2** out, int device, int width, float spacing)
+{
+    return filter_create(reinterpret_cast<Filter**>(out), 2, device, width, spacing);
+}
+extern "C" int cvs_g2_destroy(cvs_g2* h) { return filter_destroy(reinterpret_cast<Filter*>(h)); }
+extern "C" int cvs_g2_setup_host(cvs_g2* h, const float* image, int rows, int cols, size_t step)
+{
+    return filter_setup(reinterpret_cast<Filter*>(h), image, false, rows, cols, step);
+}
+extern "C" int cvs_g2_setup_host_u8(cvs_g2* h, const uint8_t* image, int rows, int cols, size_t step)
+{
+    return filter_setup(reinterpret_cast<Filter*>(h), image, true, rows, cols, step);
+}
+extern "C" int cvs_g2_size(const cvs_g2* h, int* rows, int* cols)
+{
+    if (!h) return fail(CVS_ERR_INVALID_ARG, "handle is null");
+    const Filter* f = reinterpret_cast<const Filter*>(h);
+    if (rows) *rows = f->ready ? f->rows : 0;
+    if (cols) *cols = f->ready ? f->cols : 0;
+    return CVS_OK;
+}
+extern "C" int cvs_g2_get_plane_host(cvs_g2* h, int plane, float* dst, size_t step)
+{
+    return filter_get_plane(reinterpret_cast<Filter*>(h), plane, dst, step);
+}
+
+static unsigned g2_steer_mask(float* g2, float* h2, float* e, float* mag, float* phase)
+{
+    return (g2 ? CVS_BIT(CVS_G2T) : 0u) | (h2 ? CVS_BIT(CVS_H2T) : 0u) | (e ? CVS_BIT(CVS_E) : 0u) | (mag ? CVS_BIT(CVS_MAG) : 0u) |
+           (phase ? CVS_BIT(CVS_PHASE) : 0u);
+}
+
+extern "C" int cvs_g2_steer_scalar_host(cvs_g2* h, float theta, float* g2, float* h2, float* e, float* magnitude, float* phase, size_t step)
+{
+    float* outs[CVS_G2_NPLANES] = {nullptr};
+    outs[CVS_G2T] = g2, outs[CVS_H2T] = h2, outs[CVS_E] = e, outs[CVS_MAG] = magnitude, outs[CVS_PHASE] = phase;
+    return filter_steer(reinterpret_cast<Filter*>(h), CVS_STEER_SCALAR, theta, nullptr, 0, g2_steer_mask(g2, h2, e, magnitude, phase), outs, step);
+}
+
+extern "C" int cvs_g2_steer_map_host(cvs_g2* h, const float* theta, size_t theta_step, float* g2, float* h2, float* e, float* magnitude,
+                                     float* phase, size_t step)
+{
+    float* outs[CVS_G2_NPLANES] = {nullptr};
+    outs[CVS_G2T] = g2, outs[CVS_H2T] = h2, outs[CVS_E] = e, outs[CVS_MAG] = magnitude, outs[CVS_PHASE] = phase;
+    return filter_steer(reinterpret_cast<Filter*>(h), CVS_STEER_MAP, 0.f, theta, theta_step, g2_steer_mask(g2, h2, e, magnitude, phase), outs,
+                        step);
+}
+
+extern "C" int cvs_g2_steer_point(cvs_g2* h, int x, int y, float theta, float out[5])
+{
+    Filter* f = reinterpret_cast<Filter*>(h);
+    if (!f || !out) return fail(CVS_ERR_INVALID_ARG, "null argument");
+    if (!f->ready) return fail(CVS_ERR_NOT_SETUP, "steer before setup");
+    if (x < 0 || y < 0 || x >= f->cols || y >= f->rows) return fail(CVS_ERR_INVALID_ARG, "point (%d,%d) outside %dx%d", x, y, f->cols, f->rows);
+    CU_TRY(cudaSetDevice(f->device));
+    // Fetch the 10 state values of this pixel (7 basis, c1..c3): element (y,x) of 10 consecutive planes = one strided copy.
+    float v[10];
+    const char* src = reinterpret_cast<const char*>(f->state.p) + (size_t)y * f->pitch + (size_t)x * 4;
+    CU_TRY(cudaMemcpy2DAsync(v, 4, src, f->pitch * f->rows, 4, 10, cudaMemcpyDeviceToHost, f->stream));
+    CU_TRY(cudaStreamSynchronize(f->stream));
+    // The per-point overloads are host code in the reference as well (G2.cpp:115-134): a handful of scalar flops on
+    // values read from the Mats.  Same expressions, same types.
+    float ct(std::cos(theta)), ct2(ct * ct), ct3(ct2 * ct), st(std::sin(theta)), st2(st * st), st3(st2 * st);
+    float ga(ct2), gb(-2.0 * ct * st), gc(st2);
+    float ha(ct3), hb(-3.0 * ct2 * st), hc(3.0 * ct * st2), hd(-st3);
+    const float g2 = ga * v[0] + gb * v[1] + gc * v[2];
+    const float h2 = ha * v[3] + hb * v[4] + hc * v[5] + hd * v[6];
+    float c2t(std::cos(theta * 2.0)), s2t(std::sin(theta * 2.0));
+    out[0] = g2;
+    out[1] = h2;
+    out[2] = v[7] + (c2t * v[8]) + (s2t * v[9]);
+    out[3] = std::sqrt(h2 * h2 + g2 * g2);
+    out[4] = std::atan2(h2, g2);
+    return CVS_OK;
+}
+
+// ================================ stateless point-wise ops ================================
+namespace {
+struct TempDev {  // small RAII helper for the stateless host entry points
+    void* p = nullptr;
+    ~TempDev()
+    {
+        if (p) cudaFree(p);
+    }
+};
+}  // namespace
+
+static int pointwise_host(int device, int op, int kind, const float* a, const float* b, size_t in_step, float* o1, float* o2, size_t out_step,
+                          int rows, int cols, float phi, int signum)
+{
+    if (rows <= 0 || cols <= 0) return fail(CVS_ERR_INVALID_ARG, "empty image");
+    if (in_step < (size_t)cols * 4 || out_step < (size_t)cols * 4) return fail(CVS_ERR_INVALID_ARG, "step < cols*4");
+    CU_TRY(cudaSetDevice(device));
+    const size_t pitch = align_up((size_t)cols * 4, 128), plane = pitch * rows;
+    TempDev t;
+    CU_TRY(cudaMalloc(&t.p, plane * 4));
+    float* da = static_cast<float*>(t.p);
+    float* db = reinterpret_cast<float*>(static_cast<char*>(t.p) + plane);
+    float* d1 = reinterpret_cast<float*>(static_cast<char*>(t.p) + 2 * plane);
+    float* d2 = reinterpret_cast<float*>(static_cast<char*>(t.p) + 3 * plane);
+    cudaStream_t s = nullptr;  // legacy default stream: these calls are synchronous by contract
+    if (a) CU_TRY(cudaMemcpy2DAsync(da, pitch, a, in_step, (size_t)cols * 4, rows, cudaMemcpyHostToDevice, s));
+    if (b) CU_TRY(cudaMemcpy2DAsync(db, pitch, b, in_step, (size_t)cols * 4, rows, cudaMemcpyHostToDevice, s));
+    if (op == 0)
+        CU_TRY(launch_mag_phase(da, db, pitch, o1 ? d1 : nullptr, o2 ? d2 : nullptr, pitch, rows, cols, s));
+    else
+        CU_TRY(launch_phase_maps(kind, da, db, pitch, d1, pitch, rows, cols, phi, signum, s));
+    if (o1) CU_TRY(cudaMemcpy2DAsync(o1, out_step, d1, pitch, (size_t)cols * 4, rows, cudaMemcpyDeviceToHost, s));
+    if (o2) CU_TRY(cudaMemcpy2DAsync(o2, out_step, d2, pitch, (size_t)cols * 4, rows, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    return CVS_OK;
+}
+
+extern "C" int cvs_magnitude_phase_host(int device, const float* g, const float* h, size_t in_step, float* magnitude, float* phase,
+                                        size_t out_step, int rows, int cols)
+{
+    if (!g || !h || (!magnitude && !phase)) return fail(CVS_ERR_INVALID_ARG, "null argument");
+    return pointwise_host(device, 0, 0, g, h, in_step, magnitude, phase, out_step, rows, cols, 0.f, 0);
+}
+
+extern "C" int cvs_phase_weights_host(int device, const float* phase, size_t in_step, float* lambda, size_t out_step, int rows, int cols,
+                                      float phi, int signum, float k)
+{
+    (void)k;  // unused in the reference too (G2.cpp:179-186)
+    if (!phase || !lambda) return fail(CVS_ERR_INVALID_ARG, "null argument");
+    return pointwise_host(device, 1, 0, nullptr, phase, in_step, lambda, nullptr, out_step, rows, cols, phi, signum);
+}
+
+extern "C" int cvs_find_host(int device, int kind, const float* e, const float* phase, size_t in_step, float* out, size_t out_step, int rows,
+                             int cols, float k)
+{
+    (void)k;
+    if (!e || !phase || !out || kind < 0 || kind > 2) return fail(CVS_ERR_INVALID_ARG, "bad argument");
+    return pointwise_host(device, 1, kind + 1, e, phase, in_step, out, nullptr, out_step, rows, cols, 0.f, 0);
+}
+
+// ================================ G4 ================================
+extern "C" int cvs_g4_create(cvs_g4** out, int device, int width, float spacing)
+{
+    return filter_create(reinterpret_cast<Filter**>(out), 4, device, width, spacing);
+}
+extern "C" int cvs_g4_destroy(cvs_g4* h) { return filter_destroy(reinterpret_cast<Filter*>(h)); }
+extern "C" int cvs_g4_setup_host(cvs_g4* h, const float* image, int rows, int cols, size_t step)
+{
+    return filter_setup(reinterpret_cast<Filter*>(h), image, false, rows, cols, step);
+}
+extern "C" int cvs_g4_size(const cvs_g4* h, int* rows, int* cols)
+{
+    if (!h) return fail(CVS_ERR_INVALID_ARG, "handle is null");
+    const Filter* f = reinterpret_cast<const Filter*>(h);
+    if (rows) *rows = f->ready ? f->rows : 0;
+    if (cols) *cols = f->ready ? f->cols : 0;
+    return CVS_OK;
+}
+extern "C" int cvs_g4_get_plane_host(cvs_g4* h, int plane, float* dst, size_t step)
+{
+    return filter_get_plane(reinterpret_cast<Filter*>(h), plane, dst, step);
+}
+static unsigned g4_steer_mask(float* g4, float* h4, float* mag, float* phase)
+{
+    return (g4 ? CVS_BIT(CVS_G4T) : 0u) | (h4 ? CVS_BIT(CVS_H4T) : 0u) | (mag ? CVS_BIT(CVS_MAG4) : 0u) | (phase ? CVS_BIT(CVS_PHASE4) : 0u);
+}
+extern "C" int cvs_g4_steer_scalar_host(cvs_g4* h, float theta, float* g4, float* h4, float* magnitude, float* phase, size_t step)
+{
+    float* outs[CVS_G4_NPLANES] = {nullptr};
+    outs[CVS_G4T] = g4, outs[CVS_H4T] = h4, outs[CVS_MAG4] = magnitude, outs[CVS_PHASE4] = phase;
+    return filter_steer(reinterpret_cast<Filter*>(h), CVS_STEER_SCALAR, theta, nullptr, 0, g4_steer_mask(g4, h4, magnitude, phase), outs, step);
+}
+extern "C" int cvs_g4_steer_map_host(cvs_g4* h, const float* theta, size_t theta_step, float* g4, float* h4, float* magnitude, float* phase,
+                                     size_t step)
+{
+    if (!theta) return fail(CVS_ERR_INVALID_ARG, "theta map is null");
+    float* outs[CVS_G4_NPLANES] = {nullptr};
+    outs[CVS_G4T] = g4, outs[CVS_H4T] = h4, outs[CVS_MAG4] = magnitude, outs[CVS_PHASE4] = phase;
+    return filter_steer(reinterpret_cast<Filter*>(h), CVS_STEER_MAP, 0.f, theta, theta_step, g4_steer_mask(g4, h4, magnitude, phase), outs, step);
+}
+
+// ================================ device-resident batch path ================================
+static int run_batch_dev(Filter* f, const cvs_batch* b, unsigned mask, int steer_source, float theta, const float* theta_map,
+                         float* const* outs, void* stream)
+{
+    if (!f) return fail(CVS_ERR_INVALID_ARG, "handle is null");
+    BatchGeom g;
+    int rc = geom_from_batch(b, &g);
+    if (rc) return rc;
+    rc = check_band(g, f->taps.width, g.full_rows);
+    if (rc) return rc;
+    const int nplanes = f->family == 2 ? (int)CVS_G2_NPLANES : (int)CVS_G4_NPLANES;
+    if (!mask || (mask >> nplanes)) return fail(CVS_ERR_INVALID_ARG, "mask 0x%x selects no / unknown planes", mask);
+    if (!outs) return fail(CVS_ERR_INVALID_ARG, "outs is null");
+    for (int p = 0; p < nplanes; ++p)
+        if ((mask >> p & 1u) && !outs[p]) return fail(CVS_ERR_INVALID_ARG, "outs[%d] is null but selected by mask", p);
+    if (steer_source < CVS_STEER_DOMINANT || steer_source > CVS_STEER_MAP) return fail(CVS_ERR_INVALID_ARG, "steer_source %d", steer_source);
+    if (steer_source == CVS_STEER_MAP && !theta_map) return fail(CVS_ERR_INVALID_ARG, "theta_map is null");
+    if (f->family == 4 && steer_source == CVS_STEER_DOMINANT && (mask & CVS_G4_MASK_STEER))
+        return fail(CVS_ERR_UNSUPPORTED, "G4 has no dominant orientation; pass a scalar angle or an angle map");
+    SteerSpec st{};
+    st.source = steer_source;
+    st.cos_t = std::cos(theta);
+    st.sin_t = std::sin(theta);
+    st.theta_map = theta_map;
+    return run_fused(f, g, mask, st, outs, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int cvs_g2_run_batch_dev(cvs_g2* h, const cvs_batch* b, unsigned mask, int steer_source, float theta_scalar,
+                                    const float* theta_map, float* const* outs, void* stream)
+{
+    return run_batch_dev(reinterpret_cast<Filter*>(h), b, mask, steer_source, theta_scalar, theta_map, outs, stream);
+}
+extern "C" int cvs_g4_run_batch_dev(cvs_g4* h, const cvs_batch* b, unsigned mask, int steer_source, float theta_scalar,
+                                    const float* theta_map, float* const* outs, void* stream)
+{
+    return run_batch_dev(reinterpret_cast<Filter*>(h), b, mask, steer_source, theta_scalar, theta_map, outs, stream);
+}
+
+extern "C" int cvs_pyr_down_dev(int device, const cvs_batch* b, float* out, void* stream)
+{
+    BatchGeom g;
+    int rc = geom_from_batch(b, &g);
+    if (rc) return rc;
+    if (!out) return fail(CVS_ERR_INVALID_ARG, "out is null");
+    if (b->full_rows <= 0) {  // whole frames: all rows of the output level
+        g.out_row_begin = 0;
+        g.out_row_end = (g.full_rows + 1) / 2;
+        g.out_row_origin = 0;
+    }
+    rc = check_band(g, 2, (g.full_rows + 1) / 2);
+    if (rc) return rc;
+    CU_TRY(cudaSetDevice(device));
+    CU_TRY(launch_pyr_down(g, out, static_cast<cudaStream_t>(stream)));
+    return CVS_OK;
+}
+
+// Host-buffer batch: frames are processed in chunks on two streams so that the upload of chunk i+1, the kernel of
+// chunk i and the download of chunk i-1 overlap.
+extern "C" int cvs_g2_run_batch_host(cvs_g2* h, const float* in, int n, int rows, int cols, size_t in_step, size_t in_frame_stride,
+                                     unsigned mask, float* const* outs, size_t out_step, size_t out_frame_stride)
+{
+    Filter* f = reinterpret_cast<Filter*>(h);
+    if (!f || !in || !outs) return fail(CVS_ERR_INVALID_ARG, "null argument");
+    if (n <= 0 || rows <= 0 || cols <= 0) return fail(CVS_ERR_INVALID_ARG, "n/rows/cols must be positive");
+    if (in_step < (size_t)cols * 4 || out_step < (size_t)cols * 4) return fail(CVS_ERR_INVALID_ARG, "step < cols*4");
+    if (!mask || (mask >> CVS_G2_NPLANES)) return fail(CVS_ERR_INVALID_ARG, "mask 0x%x", mask);
+    int nout = 0;
+    for (int p = 0; p < CVS_G2_NPLANES; ++p)
+        if (mask >> p & 1u) {
+            if (!outs[p]) return fail(CVS_ERR_INVALID_ARG, "outs[%d] is null but selected by mask", p);
+            ++nout;
+        }
+    CU_TRY(cudaSetDevice(f->device));
+    const size_t pitch = align_up((size_t)cols * 4, 128), fbytes = pitch * rows;
+    // chunk so that >= 4 chunks exist (pipeline depth) but each is large enough to amortise launch + copy latency
+    int chunk = (int)((64ull << 20) / fbytes);
+    if (chunk < 1) chunk = 1;
+    if (chunk > (n + 3) / 4) chunk = (n + 3) / 4;
+    if (chunk < 1) chunk = 1;
+    const int NBUF = 3;
+    CU_TRY(f->work.reserve((size_t)NBUF * chunk * fbytes * (1 + nout)));
+    static thread_local cudaStream_t streams[NBUF] = {nullptr, nullptr, nullptr};
+    for (int i = 0; i < NBUF; ++i)
+        if (!streams[i]) CU_TRY(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking));
+    SteerSpec st{};
+    st.source = CVS_STEER_DOMINANT;
+    int ci = 0;
+    for (int f0 = 0; f0 < n; f0 += chunk, ++ci) {
+        const int nf = (n - f0 < chunk) ? (n - f0) : chunk;
+        const int b = ci % NBUF;
+        cudaStream_t s = streams[b];
+        char* base = static_cast<char*>(f->work.p) + (size_t)b * chunk * fbytes * (1 + nout);
+        float* din = reinterpret_cast<float*>(base);
+        // 3-D copy: frames x rows x row-bytes
+        cudaMemcpy3DParms cp{};
+        cp.srcPtr = make_cudaPitchedPtr(const_cast<char*>(reinterpret_cast<const char*>(in)) + (size_t)f0 * in_frame_stride, in_step,
+                                        (size_t)cols * 4, in_frame_stride / in_step);
+        cp.dstPtr = make_cudaPitchedPtr(din, pitch, (size_t)cols * 4, rows);
+        cp.extent = make_cudaExtent((size_t)cols * 4, rows, nf);
+        cp.kind = cudaMemcpyHostToDevice;
+        if (in_frame_stride % in_step == 0) {
+            CU_TRY(cudaMemcpy3DAsync(&cp, s));
+        } else {
+            for (int k = 0; k < nf; ++k)
+                CU_TRY(cudaMemcpy2DAsync(reinterpret_cast<char*>(din) + (size_t)k * fbytes, pitch,
+                                         reinterpret_cast<const char*>(in) + (size_t)(f0 + k) * in_frame_stride, in_step, (size_t)cols * 4,
+                                         rows, cudaMemcpyHostToDevice, s));
+        }
+        float* douts[CVS_G2_NPLANES] = {nullptr};
+        int slot = 0;
+        for (int p = 0; p < CVS_G2_NPLANES; ++p)
+            if (mask >> p & 1u) douts[p] = reinterpret_cast<float*>(base + (size_t)(1 + slot++) * chunk * fbytes);
+        BatchGeom g = whole_frame_geom(din, false, nf, rows, cols, pitch, fbytes, pitch, fbytes);
+        int rc = run_fused(f, g, mask, st, douts, s);
+        if (rc) return rc;
+        for (int p = 0; p < CVS_G2_NPLANES; ++p)
+            if (mask >> p & 1u) {
+                char* dst = reinterpret_cast<char*>(outs[p]) + (size_t)f0 * out_frame_stride;
+                if (out_frame_stride % out_step == 0) {
+                    cudaMemcpy3DParms cq{};
+                    cq.srcPtr = make_cudaPitchedPtr(douts[p], pitch, (size_t)cols * 4, rows);
+                    cq.dstPtr = make_cudaPitchedPtr(dst, out_step, (size_t)cols * 4, out_frame_stride / out_step);
+                    cq.extent = make_cudaExtent((size_t)cols * 4, rows, nf);
+                    cq.kind = cudaMemcpyDeviceToHost;
+                    CU_TRY(cudaMemcpy3DAsync(&cq, s));
+                } else {
+                    for (int k = 0; k < nf; ++k)
+                        CU_TRY(cudaMemcpy2DAsync(dst + (size_t)k * out_frame_stride, out_step, reinterpret_cast<char*>(douts[p]) + (size_t)k * fbytes,
+                                                 pitch, (size_t)cols * 4, rows, cudaMemcpyDeviceToHost, s));
+                }
+            }
+    }
+    for (int i = 0; i < NBUF; ++i) CU_TRY(cudaStreamSynchronize(streams[i]));
+    return CVS_OK;
+}
+
+// ================================ measurement helpers ================================
+extern "C" int cvs_bench_ffma(int device, int form, int iters, double* instr_per_s, float* elapsed_ms)
+{
+    if (form < 0 || form > 2 || iters <= 0 || !instr_per_s) return fail(CVS_ERR_INVALID_ARG, "bad argument");
+    CU_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    const int threads = 256, blocks = prop.multiProcessorCount * 8;
+    float* sink = nullptr;
+    CU_TRY(cudaMalloc(&sink, 4));
+    cudaEvent_t e0, e1;
+    CU_TRY(cudaEventCreate(&e0));
+    CU_TRY(cudaEventCreate(&e1));
+    CU_TRY(launch_ffma_bench(form, iters / 8 + 1, blocks, threads, sink, nullptr));  // warm-up
+    CU_TRY(cudaEventRecord(e0, nullptr));
+    CU_TRY(launch_ffma_bench(form, iters, blocks, threads, sink, nullptr));
+    CU_TRY(cudaEventRecord(e1, nullptr));
+    CU_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    const double n = (double)blocks * threads * (double)iters * 64.0;  // 4 x 16 FFMA per iteration per thread
+    *instr_per_s = n / (ms * 1e-3);
+    if (elapsed_ms) *elapsed_ms = ms;
+    return CVS_OK;
+}
+
+extern "C" int cvs_g2_last_launch(const cvs_g2* h, int* grid_xyz, int* block, int* smem, char* name, int name_len)
+{
+    if (!h) return fail(CVS_ERR_INVALID_ARG, "handle is null");
+    const Filter* f = reinterpret_cast<const Filter*>(h);
+    if (grid_xyz) memcpy(grid_xyz, f->last.grid, sizeof(int) * 3);
+    if (block) *block = f->last.block;
+    if (smem) *smem = f->last.smem;
+    if (name && name_len > 0) snprintf(name, (size_t)name_len, "%s", f->last.name);
+    return CVS_OK;
+}
+
+extern "C" unsigned long long cvs_launch_count(void) { return launch_count(); }

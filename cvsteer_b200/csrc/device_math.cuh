@@ -1,0 +1,133 @@
+// Point-wise math shared by every kernel: the orientation analysis, steering weights, magnitude /
+// phase and phase-weight maps of the reference, with OpenCV-compatible atan2.
+//
+// Reference lines restated here (cvsteer/SteerableFiltersG2.cpp unless noted):
+//   products + C1,C2,C3 ............ :70-95
+//   dominant angle + strength ...... :97-99  (+ SteerableFilters::wrap, SteerableFilters.cpp:46-51)
+//   steering weights ............... :140-144 (G2), SteerableFiltersG4.cpp:116-121 (G4)
+//   magnitude / phase .............. :107-112
+//   oriented energy ................ :163-164, :174-176
+//   phase weights / find* .......... :179-212
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace cvs {
+namespace dev {
+
+// BORDER_REFLECT_101 index folding, iterated so that images smaller than the filter radius behave like
+// cv::borderInterpolate (a size-1 dimension maps every index to 0).
+__host__ __device__ __forceinline__ int reflect101(int p, int n)
+{
+    if (n == 1) return 0;
+    while (p < 0 || p >= n) p = (p < 0) ? -p : 2 * (n - 1) - p;
+    return p;
+}
+
+// cv::cartToPolar's angle (hal::fastAtan32f, in radians, range [0, 2pi)): 7th-order odd polynomial in
+// min/max, evaluated with FMAs as OpenCV's SIMD path does.  Verified bit-identical to cv2 4.13.0 on 2M
+// random points when evaluated this way (tests/test_device_math_model.py holds the numpy model).
+__device__ __forceinline__ float cv_atan2(float y, float x)
+{
+    constexpr float kDeg = 57.29577951308232f;  // (float)(180/CV_PI)
+    constexpr float P1 = 0.9997878412794807f * kDeg;
+    constexpr float P3 = -0.3258083974640975f * kDeg;
+    constexpr float P5 = 0.1555786518463281f * kDeg;
+    constexpr float P7 = -0.04432655554792128f * kDeg;
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float c = __fdiv_rn(mn, mx + 2.220446049250313e-16f);  // + (float)DBL_EPSILON: (0,0) -> 0
+    const float c2 = c * c;
+    float a = fmaf(fmaf(fmaf(P7, c2, P5), c2, P3), c2, P1) * c;
+    a = (ay > ax) ? 90.f - a : a;
+    a = (x < 0.f) ? 180.f - a : a;
+    a = (y < 0.f) ? 360.f - a : a;
+    // NaN inputs: fmaxf/fminf drop NaNs, so force the NaN through as cv does (c = NaN there)
+    a = (x != x || y != y) ? __int_as_float(0x7fc00000) : a;
+    return a * 0.017453292519943295f;  // (float)(CV_PI/180)
+}
+
+// cv::cartToPolar's magnitude: sqrt(x*x + y*y) with the inner sum fused, IEEE sqrt.
+__device__ __forceinline__ float cv_magnitude(float x, float y) { return __fsqrt_rn(fmaf(x, x, y * y)); }
+
+// SteerableFilters::wrap: a > float(pi) -> float(double(a) - 2pi).  float(2pi) = 2pi + 1.7484555e-7, the
+// first subtraction is exact (Sterbenz), the correction restores the double-precision result.
+__device__ __forceinline__ float wrap_pi(float a)
+{
+    return (a > 3.14159274101257324f) ? (a - 6.28318548202514648f) + 1.7484555e-7f : a;
+}
+
+struct Orientation {
+    float c1, c2, c3, strength, theta;
+};
+
+// G2.cpp:70-99 on the 7 basis values of one pixel.
+__device__ __forceinline__ Orientation orientation_g2(float a, float b, float c, float ha, float hb, float hc,
+                                                     float hd)
+{
+    Orientation o;
+    const float aa = a * a, cc = c * c, haa = ha * ha, hdd = hd * hd, hbb = hb * hb, hcc = hc * hc;
+    const float hac = ha * hc, hbd = hb * hd;
+    float c1 = 0.5f * (b * b);
+    c1 = fmaf(0.25f, a * c, c1);
+    c1 = fmaf(0.375f, aa + cc, c1);
+    c1 = fmaf(0.3125f, haa + hdd, c1);
+    c1 = fmaf(0.5625f, hbb + hcc, c1);
+    c1 = fmaf(0.375f, hac + hbd, c1);
+    float c2 = 0.5f * (aa - cc);
+    c2 = fmaf(0.46875f, haa - hdd, c2);
+    c2 = fmaf(0.28125f, hbb - hcc, c2);
+    c2 = fmaf(0.1875f, hac - hbd, c2);
+    float c3 = -(a * b) - b * c;
+    c3 = fmaf(-0.9375f, fmaf(hc, hd, ha * hb), c3);
+    c3 = fmaf(-1.6875f, hb * hc, c3);
+    c3 = fmaf(-0.1875f, ha * hd, c3);
+    o.c1 = c1;
+    o.c2 = c2;
+    o.c3 = c3;
+    o.strength = cv_magnitude(c2, c3);
+    o.theta = 0.5f * wrap_pi(cv_atan2(c3, c2));
+    return o;
+}
+
+// G2.cpp:140-144 / :151-154
+__device__ __forceinline__ void steer_g2(float ct, float st, float a, float b, float c, float ha, float hb,
+                                         float hc, float hd, float& g2, float& h2)
+{
+    const float ct2 = ct * ct, st2 = st * st, cs = ct * st;
+    g2 = fmaf(ct2, a, fmaf(-2.f * cs, b, st2 * c));
+    h2 = fmaf(ct2 * ct, ha, fmaf(-3.f * ct2 * st, hb, fmaf(3.f * ct * st2, hc, -(st2 * st) * hd)));
+}
+
+// G4.cpp:97-111 / :116-121
+__device__ __forceinline__ void steer_g4(float ct, float st, const float* g /*5*/, const float* h /*6*/, float& g4,
+                                         float& h4)
+{
+    const float ct2 = ct * ct, ct3 = ct2 * ct, ct4 = ct3 * ct, ct5 = ct4 * ct;
+    const float st2 = st * st, st3 = st2 * st, st4 = st3 * st, st5 = st4 * st;
+    g4 = fmaf(ct4, g[0], fmaf(-4.f * ct3 * st, g[1], fmaf(6.f * ct2 * st2, g[2], fmaf(-4.f * ct * st3, g[3], st4 * g[4]))));
+    h4 = fmaf(ct5, h[0],
+              fmaf(-5.f * ct4 * st, h[1],
+                   fmaf(10.f * ct3 * st2, h[2], fmaf(-10.f * ct2 * st3, h[3], fmaf(5.f * ct * st4, h[4], -st5 * h[5])))));
+}
+
+// G2.cpp:107-112
+__device__ __forceinline__ void magnitude_phase(float g, float h, float& mag, float& phase)
+{
+    mag = cv_magnitude(g, h);
+    float p = wrap_pi(cv_atan2(h, g));
+    phase = (p != p) ? 0.f : p;  // cv::patchNaNs
+}
+
+// G2.cpp:179-186: lambda = cos^2(err) gated at pi/2.
+__device__ __forceinline__ float phase_weight(float phase, float phi, bool signum)
+{
+    float err = signum ? fabsf(phase - phi) : fabsf(fabsf(phase) - fabsf(phi));
+    const float alt = (6.28318548202514648f - err) - 1.7484555e-7f;  // float(2*M_PI - err)
+    err = fminf(err, alt);
+    const float ct = cosf(err);
+    return (fabsf(err) > 1.57079637050628662f) ? 0.f : ct * ct;
+}
+
+}  // namespace dev
+}  // namespace cvs

@@ -1,0 +1,380 @@
+// Kernel instantiations and host launchers.  sm_100a only.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <utility>
+
+#include "march_launch.cuh"
+
+namespace cvs {
+
+std::atomic<unsigned long long> g_launches{0};
+unsigned long long launch_count() { return g_launches.load(); }
+
+// ------------------------------------------------------------------------------------------------
+// Generic-width path (width != family default): two simple kernels through a scratch buffer.
+// Correct for any 1 <= width <= MAX_WIDTH and any image size; not the tuned path.
+// ------------------------------------------------------------------------------------------------
+template <int NSETS>
+struct WideTaps {
+    int width;
+    float t[NSETS][MAX_TAPS];  // t[s][i + width], i = -width..width
+};
+
+template <class Fam, typename TIn>
+__global__ void k_generic_rows(const __grid_constant__ MarchArgs a, const __grid_constant__ WideTaps<Fam::NSETS> taps, float* tmp, int frame)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;  // buffer row
+    if (x >= a.cols) return;
+    const TIn* src = reinterpret_cast<const TIn*>(reinterpret_cast<const char*>(a.in) + (long long)frame * a.in_frame_stride +
+                                                  (long long)r * a.in_pitch);
+    const int w = taps.width;
+    float acc[Fam::NROW];
+#pragma unroll
+    for (int p = 0; p < Fam::NROW; ++p) acc[p] = 0.f;
+    for (int i = -w; i <= w; ++i) {
+        const float v = (float)src[dev::reflect101(x + i, a.cols)];
+#pragma unroll
+        for (int p = 0; p < Fam::NROW; ++p) acc[p] = fmaf(taps.t[Fam::row_set(p)][i + w], v, acc[p]);
+    }
+    const size_t plane = (size_t)a.buf_rows * a.cols;
+#pragma unroll
+    for (int p = 0; p < Fam::NROW; ++p) tmp[p * plane + (size_t)r * a.cols + x] = acc[p];
+}
+
+template <class Fam>
+__global__ void k_generic_cols(const __grid_constant__ MarchArgs a, const __grid_constant__ WideTaps<Fam::NSETS> taps, const float* tmp,
+                               int frame)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = a.out_row_begin + blockIdx.y;
+    if (x >= a.cols) return;
+    const int w = taps.width;
+    const size_t plane = (size_t)a.buf_rows * a.cols;
+    float b[Fam::NBASIS];
+#pragma unroll
+    for (int q = 0; q < Fam::NBASIS; ++q) b[q] = 0.f;
+    for (int i = -w; i <= w; ++i) {
+        const int r = dev::reflect101(y + i, a.full_rows) - a.y_origin;
+        float v[Fam::NROW];
+#pragma unroll
+        for (int p = 0; p < Fam::NROW; ++p) v[p] = (r >= 0 && r < a.buf_rows) ? tmp[p * plane + (size_t)r * a.cols + x] : 0.f;
+#pragma unroll
+        for (int q = 0; q < Fam::NBASIS; ++q) b[q] = fmaf(taps.t[Fam::basis_set(q)][i + w], v[Fam::basis_row(q)], b[q]);
+    }
+    const long long row_off = (long long)frame * a.out_frame_stride + (long long)(y - a.out_row_origin) * a.out_pitch;
+    Fam::template epilogue<0>(b, a, row_off, x);
+}
+
+template <class Fam>
+static cudaError_t launch_generic(const FamilyTaps& ft, const BatchGeom& g, const MarchArgs& a, float* scratch, cudaStream_t stream,
+                                  LaunchInfo* info)
+{
+    if (!scratch) return cudaErrorInvalidValue;
+    WideTaps<Fam::NSETS> wt;
+    memset(&wt, 0, sizeof(wt));
+    wt.width = ft.width;
+    for (int api = 0; api < ft.nsets; ++api) memcpy(wt.t[Fam::unique_of(api)], ft.t[api], sizeof(float) * (2 * ft.width + 1));
+    const dim3 block(128);
+    const dim3 grid_r((g.cols + 127) / 128, g.buf_rows), grid_c((g.cols + 127) / 128, g.out_row_end - g.out_row_begin);
+    for (int f = 0; f < g.n; ++f) {
+        if (g.in_u8)
+            k_generic_rows<Fam, unsigned char><<<grid_r, block, 0, stream>>>(a, wt, scratch, f);
+        else
+            k_generic_rows<Fam, float><<<grid_r, block, 0, stream>>>(a, wt, scratch, f);
+        k_generic_cols<Fam><<<grid_c, block, 0, stream>>>(a, wt, scratch, f);
+        g_launches.fetch_add(2);
+    }
+    if (info) {
+        info->grid[0] = grid_c.x, info->grid[1] = grid_c.y, info->grid[2] = 1;
+        info->block = 128;
+        info->smem = 0;
+        snprintf(info->name, sizeof(info->name), "generic_w%d", ft.width);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_march_g2(const FamilyTaps&, const BatchGeom&, const MarchArgs&, bool dominant, cudaStream_t, LaunchInfo*);
+cudaError_t launch_march_g4(const FamilyTaps&, const BatchGeom&, const MarchArgs&, bool dominant, cudaStream_t, LaunchInfo*);
+
+bool uses_march_path(int family, int width) { return (family == 2 && width == G2Fam::R) || (family == 4 && width == G4Fam::R); }
+
+size_t scratch_bytes_generic(int family, const BatchGeom& g)
+{
+    const int nrow = family == 2 ? G2Fam::NROW : G4Fam::NROW;
+    return (size_t)nrow * g.buf_rows * g.cols * sizeof(float);
+}
+
+cudaError_t launch_basis_fused(int family, const FamilyTaps& taps, const BatchGeom& g, unsigned mask, const SteerSpec& st,
+                               float* const* outs, float* scratch, cudaStream_t stream, LaunchInfo* info)
+{
+    const int nplanes = family == 2 ? (int)CVS_G2_NPLANES : (int)CVS_G4_NPLANES;
+    const MarchArgs a = make_args(g, mask, st, outs, nplanes);
+    const int out_rows = g.out_row_end - g.out_row_begin;
+    if (out_rows <= 0 || g.cols <= 0 || g.n <= 0) return cudaErrorInvalidValue;
+    if (!uses_march_path(family, taps.width)) {
+        return family == 2 ? launch_generic<G2Fam>(taps, g, a, scratch, stream, info)
+                           : launch_generic<G4Fam>(taps, g, a, scratch, stream, info);
+    }
+    if (g.n > 65535) return cudaErrorInvalidValue;  // callers split larger batches
+    return family == 2 ? launch_march_g2(taps, g, a, st.source == CVS_STEER_DOMINANT, stream, info)
+                       : launch_march_g4(taps, g, a, st.source == CVS_STEER_DOMINANT, stream, info);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Point-wise kernels on materialised planes (class-API steer()/find*() calls)
+// ------------------------------------------------------------------------------------------------
+struct PlaneSteerArgs {
+    const float* p[16];
+    long long pitch, theta_pitch, out_pitch;
+    int rows, cols;
+    int source;
+    float cos_t, sin_t, cos2t, sin2t;
+    const float* theta;
+    unsigned mask;
+    float* out[MARCH_MAX_OUT];
+};
+
+template <typename T>
+__device__ __forceinline__ T& at(T* base, long long pitch, int y, int x)
+{
+    return *reinterpret_cast<T*>(reinterpret_cast<char*>(const_cast<typename std::remove_const<T>::type*>(base)) + (long long)y * pitch +
+                                 4ll * x);
+}
+
+// steer(theta, g2, h2[, e, magnitude, phase]) from the stored class state -- G2.cpp:137-177
+__global__ void k_g2_steer_planes(const __grid_constant__ PlaneSteerArgs a)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= a.cols) return;
+    float b[7];
+#pragma unroll
+    for (int q = 0; q < 7; ++q) b[q] = at(a.p[q], a.pitch, y, x);
+    float ct, st, c2t, s2t;
+    if (a.source == CVS_STEER_SCALAR) {
+        ct = a.cos_t, st = a.sin_t, c2t = a.cos2t, s2t = a.sin2t;
+    } else {
+        const float th = at(a.theta, a.theta_pitch, y, x);
+        sincosf(th, &st, &ct);
+        c2t = fmaf(ct, ct, -st * st);
+        s2t = 2.f * ct * st;
+    }
+    float g2, h2;
+    dev::steer_g2(ct, st, b[0], b[1], b[2], b[3], b[4], b[5], b[6], g2, h2);
+    const unsigned m = a.mask;
+    if (m & CVS_BIT(CVS_G2T)) at(a.out[CVS_G2T], a.out_pitch, y, x) = g2;
+    if (m & CVS_BIT(CVS_H2T)) at(a.out[CVS_H2T], a.out_pitch, y, x) = h2;
+    if (m & CVS_BIT(CVS_E)) {
+        const float c1 = at(a.p[CVS_C1], a.pitch, y, x), c2 = at(a.p[CVS_C2], a.pitch, y, x), c3 = at(a.p[CVS_C3], a.pitch, y, x);
+        at(a.out[CVS_E], a.out_pitch, y, x) = fmaf(c2, c2t, fmaf(c3, s2t, c1));
+    }
+    if (m & (CVS_BIT(CVS_MAG) | CVS_BIT(CVS_PHASE))) {
+        float mag, ph;
+        dev::magnitude_phase(g2, h2, mag, ph);
+        if (m & CVS_BIT(CVS_MAG)) at(a.out[CVS_MAG], a.out_pitch, y, x) = mag;
+        if (m & CVS_BIT(CVS_PHASE)) at(a.out[CVS_PHASE], a.out_pitch, y, x) = ph;
+    }
+}
+
+// steer(theta, g4, h4) -- G4.cpp:92-122 (+ magnitude/phase per the G2 definition)
+__global__ void k_g4_steer_planes(const __grid_constant__ PlaneSteerArgs a)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= a.cols) return;
+    float b[11];
+#pragma unroll
+    for (int q = 0; q < 11; ++q) b[q] = at(a.p[q], a.pitch, y, x);
+    float ct, st;
+    if (a.source == CVS_STEER_SCALAR) {
+        ct = a.cos_t, st = a.sin_t;
+    } else {
+        sincosf(at(a.theta, a.theta_pitch, y, x), &st, &ct);
+    }
+    float g4, h4;
+    dev::steer_g4(ct, st, &b[0], &b[5], g4, h4);
+    const unsigned m = a.mask;
+    if (m & CVS_BIT(CVS_G4T)) at(a.out[CVS_G4T], a.out_pitch, y, x) = g4;
+    if (m & CVS_BIT(CVS_H4T)) at(a.out[CVS_H4T], a.out_pitch, y, x) = h4;
+    if (m & (CVS_BIT(CVS_MAG4) | CVS_BIT(CVS_PHASE4))) {
+        float mag, ph;
+        dev::magnitude_phase(g4, h4, mag, ph);
+        if (m & CVS_BIT(CVS_MAG4)) at(a.out[CVS_MAG4], a.out_pitch, y, x) = mag;
+        if (m & CVS_BIT(CVS_PHASE4)) at(a.out[CVS_PHASE4], a.out_pitch, y, x) = ph;
+    }
+}
+
+static PlaneSteerArgs make_psa(const PlaneSet& ps, int rows, int cols, const SteerSpec& st, float c2t, float s2t, size_t theta_pitch,
+                               unsigned mask, float* const* outs, size_t out_pitch, int nplanes)
+{
+    PlaneSteerArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int i = 0; i < 16; ++i) a.p[i] = ps.p[i];
+    a.pitch = (long long)ps.pitch;
+    a.theta_pitch = (long long)theta_pitch;
+    a.out_pitch = (long long)out_pitch;
+    a.rows = rows, a.cols = cols;
+    a.source = st.source;
+    a.cos_t = st.cos_t, a.sin_t = st.sin_t, a.cos2t = c2t, a.sin2t = s2t;
+    a.theta = st.theta_map;
+    a.mask = mask;
+    for (int p = 0; p < nplanes; ++p) a.out[p] = (mask >> p & 1u) ? outs[p] : nullptr;
+    return a;
+}
+
+cudaError_t launch_g2_steer_planes(const PlaneSet& state, int rows, int cols, const SteerSpec& st, float cos2t, float sin2t,
+                                   size_t theta_pitch, unsigned mask, float* const* outs, size_t out_pitch, cudaStream_t stream)
+{
+    const PlaneSteerArgs a = make_psa(state, rows, cols, st, cos2t, sin2t, theta_pitch, mask, outs, out_pitch, CVS_G2_NPLANES);
+    k_g2_steer_planes<<<dim3((cols + 127) / 128, rows), 128, 0, stream>>>(a);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_g4_steer_planes(const PlaneSet& basis, int rows, int cols, const SteerSpec& st, size_t theta_pitch, unsigned mask,
+                                   float* const* outs, size_t out_pitch, cudaStream_t stream)
+{
+    const PlaneSteerArgs a = make_psa(basis, rows, cols, st, 0.f, 0.f, theta_pitch, mask, outs, out_pitch, CVS_G4_NPLANES);
+    k_g4_steer_planes<<<dim3((cols + 127) / 128, rows), 128, 0, stream>>>(a);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
+__global__ void k_mag_phase(const float* g, const float* h, long long in_pitch, float* mag, float* phase, long long out_pitch, int cols)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= cols) return;
+    float m, p;
+    dev::magnitude_phase(at(g, in_pitch, y, x), at(h, in_pitch, y, x), m, p);
+    if (mag) at(mag, out_pitch, y, x) = m;
+    if (phase) at(phase, out_pitch, y, x) = p;
+}
+
+cudaError_t launch_mag_phase(const float* g, const float* h, size_t in_pitch, float* mag, float* phase, size_t out_pitch, int rows,
+                             int cols, cudaStream_t stream)
+{
+    k_mag_phase<<<dim3((cols + 127) / 128, rows), 128, 0, stream>>>(g, h, (long long)in_pitch, mag, phase, (long long)out_pitch, cols);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
+__global__ void k_phase_maps(int kind, const float* e, const float* phase, long long in_pitch, float* out, long long out_pitch, int cols,
+                             float phi, int signum)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= cols) return;
+    const float lam = dev::phase_weight(at(phase, in_pitch, y, x), phi, signum != 0);
+    at(out, out_pitch, y, x) = kind == 0 ? lam : at(e, in_pitch, y, x) * lam;
+}
+
+cudaError_t launch_phase_maps(int kind, const float* e, const float* phase, size_t in_pitch, float* out, size_t out_pitch, int rows,
+                              int cols, float phi, int signum, cudaStream_t stream)
+{
+    // G2.cpp:201-212: edges (pi/2, unsigned), dark lines (0, signed), bright lines (pi, signed)
+    if (kind == 1) phi = 1.57079637050628662f, signum = 0;
+    if (kind == 2) phi = 0.f, signum = 1;
+    if (kind == 3) phi = 3.14159274101257324f, signum = 1;
+    k_phase_maps<<<dim3((cols + 127) / 128, rows), 128, 0, stream>>>(kind, e, phase, (long long)in_pitch, out, (long long)out_pitch, cols,
+                                                                     phi, signum);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pyramid: cv::pyrDown semantics.  One thread per output pixel; the 5x5 window is gathered through L1.
+// Arithmetic order follows OpenCV's float path: rows  6*c + 4*(l1+r1) + l2 + r2, then the same down
+// the column, one multiply by 1/256 at the end.
+// ------------------------------------------------------------------------------------------------
+template <typename TIn>
+__global__ void k_pyr_down(const __grid_constant__ MarchArgs a, float* out, int out_cols)
+{
+    const int xo = blockIdx.x * blockDim.x + threadIdx.x;
+    const int yo = a.out_row_begin + blockIdx.y;
+    const int frame = blockIdx.z;
+    if (xo >= out_cols) return;
+    const char* base = reinterpret_cast<const char*>(a.in) + (long long)frame * a.in_frame_stride;
+    int xs[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) xs[i] = dev::reflect101(2 * xo + i - 2, a.cols);
+    float r[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const int gy = dev::reflect101(2 * yo + j - 2, a.full_rows) - a.y_origin;
+        const TIn* src = reinterpret_cast<const TIn*>(base + (long long)gy * a.in_pitch);
+        const float v0 = (float)src[xs[0]], v1 = (float)src[xs[1]], v2 = (float)src[xs[2]], v3 = (float)src[xs[3]], v4 = (float)src[xs[4]];
+        r[j] = v2 * 6.f + (v1 + v3) * 4.f + v0 + v4;
+    }
+    const float v = (r[2] * 6.f + (r[1] + r[3]) * 4.f + r[0] + r[4]) * (1.f / 256.f);
+    *reinterpret_cast<float*>(reinterpret_cast<char*>(out) + (long long)frame * a.out_frame_stride +
+                              (long long)(yo - a.out_row_origin) * a.out_pitch + 4ll * xo) = v;
+}
+
+cudaError_t launch_pyr_down(const BatchGeom& g, float* out, cudaStream_t stream)
+{
+    SteerSpec st{};
+    MarchArgs a = make_args(g, 0, st, nullptr, 0);
+    const int out_cols = (g.cols + 1) / 2;
+    const int out_rows = g.out_row_end - g.out_row_begin;
+    if (out_rows <= 0 || g.n <= 0 || g.n > 65535) return cudaErrorInvalidValue;
+    const dim3 grid((out_cols + 127) / 128, out_rows, g.n);
+    if (g.in_u8)
+        k_pyr_down<unsigned char><<<grid, 128, 0, stream>>>(a, out, out_cols);
+    else
+        k_pyr_down<float><<<grid, 128, 0, stream>>>(a, out, out_cols);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP32 roofline denominator: a saturating FFMA loop in the three operand forms the stencil can use.
+// ------------------------------------------------------------------------------------------------
+struct FfmaConsts {
+    float c[16];
+};
+
+// The stencil's inner instruction is  acc = fma(value, tap, acc)  with value/acc in registers and the tap either an
+// immediate (FORM 0), a third register (FORM 1) or a constant-bank operand (FORM 2, how k_march takes its taps).
+template <int FORM>
+__global__ void __launch_bounds__(256) k_ffma(const __grid_constant__ FfmaConsts k, int iters, float* sink, float seed)
+{
+    float acc[16], v[8], r[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = seed + threadIdx.x * 1e-6f + i;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = seed + 1e-3f * (float)(threadIdx.x + i);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = k.c[i] + seed;  // run-time taps held in registers (FORM 1)
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float val = v[(i + u) & 7];
+                if (FORM == 0) acc[i] = fmaf(val, 0.25f + 0.03125f * (float)(i + 1) - 0.125f * (float)u, acc[i]);
+                else if (FORM == 1) acc[i] = fmaf(val, r[(i + 5 * u) & 15], acc[i]);
+                else acc[i] = fmaf(val, k.c[(i + 5 * u) & 15], acc[i]);
+            }
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += acc[i];
+    if (s == 123.456f) sink[0] = s;  // keeps the loop alive; never true in practice
+}
+
+cudaError_t launch_ffma_bench(int form, int iters, int blocks, int threads, float* sink, cudaStream_t stream)
+{
+    FfmaConsts k;
+    for (int i = 0; i < 16; ++i) k.c[i] = (i & 1 ? -1.f : 1.f) * (0.25f + 0.03125f * i);
+    if (form == 0) k_ffma<0><<<blocks, threads, 0, stream>>>(k, iters, sink, 0.f);
+    else if (form == 1) k_ffma<1><<<blocks, threads, 0, stream>>>(k, iters, sink, 0.f);
+    else k_ffma<2><<<blocks, threads, 0, stream>>>(k, iters, sink, 0.f);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
+}  // namespace cvs

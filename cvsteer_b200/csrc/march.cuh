@@ -1,0 +1,291 @@
+// Fused separable-basis "marching" kernel for sm_100a.
+//
+// One CTA owns a strip of TW image columns and a band of BH image rows of one frame.
+//   1. The input tile (band + R halo rows/cols each side) is staged ONCE into shared memory: a single
+//      TMA tensor copy (cp.async.bulk.tensor.3d + mbarrier) for tiles the tensor map can describe, with
+//      BORDER_REFLECT_101 halos patched in shared memory afterwards (TMA can only zero-fill), or a
+//      cooperative reflect-indexed load for unaligned / tiny / 8-bit inputs.
+//   2. Each thread owns one column and marches down the band.  Per row it runs ALL unique row passes from
+//      2R+1 shared-memory reads (even/odd tap symmetry: R adds + R subs shared by every filter), pushes
+//      the results into a (2R+1)-row register window per row-filtered plane, then runs ALL column passes
+//      from registers.  No intermediate ever touches shared or global memory.
+//   3. The family's epilogue (orientation analysis, steering, energy, magnitude, phase ...) runs on the
+//      basis values still in registers and stores only the selected planes, one coalesced 128 B line
+//      per warp per plane.
+//
+// This replaces the reference's 7 (G2) / 11 (G4) full-image cv::sepFilter2D passes plus ~40 full-image
+// Mat temporaries (cvsteer/SteerableFiltersG2.cpp:62-99, SteerableFiltersG4.cpp:69-80) by one pass that
+// reads each input pixel from HBM once and writes each selected output once.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <utility>
+
+#include "device_math.cuh"
+
+namespace cvs {
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + TMA (no CUTLASS dependency)
+// ------------------------------------------------------------------------------------------------
+namespace ptx {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int x, int y, int z, uint64_t* bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+}  // namespace ptx
+
+// ------------------------------------------------------------------------------------------------
+// Kernel arguments
+// ------------------------------------------------------------------------------------------------
+enum { MARCH_TW = 128, MARCH_MAX_OUT = 20 };
+// TMA needs every box row to START on a 16-byte boundary of global memory, i.e. the innermost start coordinate must be
+// a multiple of 4 floats (x0 - 6 faults with "illegal instruction"; x0 - 4 and x0 - 8 are fine).  So the tile's left
+// halo is the radius rounded up to 4 floats, and the row pitch follows.
+__host__ __device__ constexpr int march_halo_left(int R) { return (R + 3) & ~3; }
+__host__ __device__ constexpr int march_tile_width(int R) { return MARCH_TW + 2 * march_halo_left(R); }
+
+struct MarchArgs {
+    // input: n frames, rows are buffer rows; element (f, r, c) at in + f*in_frame_stride + r*in_pitch + c (bytes for
+    // pitch/stride).  The buffer holds image rows [y_origin, y_origin + buf_rows) of an image full_rows tall.
+    const void* in;
+    long long in_pitch, in_frame_stride;   // bytes
+    int cols, full_rows, buf_rows, y_origin;
+    int out_row_begin, out_row_end, out_row_origin;  // image rows to produce; output buffer row = y - out_row_origin
+    long long out_pitch, out_frame_stride;           // bytes
+    unsigned mask;
+    int steer_source;          // cvs_steer_source
+    float cos_t, sin_t;        // scalar steering angle
+    const float* theta_map;    // per-pixel angle map in output layout (steer_source == MAP)
+    float* out[MARCH_MAX_OUT];
+};
+
+// Tap tables passed BY VALUE as a kernel parameter: they live in the constant bank, so every FFMA takes
+// its tap as a constant-bank operand (no register, no global state shared between handles).
+// t[s][i] = tap i (i = 0..R) of unique tap set s; odd sets have t[s][0] == 0.
+template <int NSETS, int R>
+struct TapTable {
+    float t[NSETS][R + 1];
+};
+
+// ------------------------------------------------------------------------------------------------
+// Tile loaders
+// ------------------------------------------------------------------------------------------------
+// Patch BORDER_REFLECT_101 halos of a TMA-loaded (zero-filled) tile in place.  Requires cols >= R+1 and
+// full_rows >= R+1 so that one fold lands inside the tile (host guarantees; smaller images take the manual path).
+template <int R, int TWH, int TROWS>
+__device__ __forceinline__ void patch_reflect(float* tile, int x0, int ytop, int cols, int full_rows, int nthreads)
+{
+    constexpr int HL = march_halo_left(R);  // tile column 0 is image column x0 - HL
+    const bool fix_l = (x0 - R) < 0, fix_r = (x0 + MARCH_TW + R) > cols;
+    const bool fix_t = ytop < 0, fix_b = (ytop + TROWS) > full_rows;
+    if (!(fix_l || fix_r || fix_t || fix_b)) return;  // CTA-uniform
+    if (fix_l || fix_r) {
+        for (int i = threadIdx.x; i < TROWS * 2 * R; i += nthreads) {
+            const int rt = i / (2 * R), k = i % (2 * R);
+            const int gx = (k < R) ? (k - R) : (cols + (k - R));  // -R..-1, cols..cols+R-1
+            const int ct = gx - (x0 - HL);
+            const bool need = (k < R) ? fix_l : (fix_r && ct < TWH);
+            if (need && ct >= 0) {
+                const int sx = (gx < 0 ? -gx : 2 * (cols - 1) - gx) - (x0 - HL);
+                tile[rt * TWH + ct] = tile[rt * TWH + sx];
+            }
+        }
+        __syncthreads();
+    }
+    if (fix_t || fix_b) {
+        for (int i = threadIdx.x; i < 2 * R * TWH; i += nthreads) {
+            const int k = i / TWH, ct = i % TWH;
+            const int gy = (k < R) ? (k - R) : (full_rows + (k - R));
+            const int rt = gy - ytop;
+            const bool need = (k < R) ? fix_t : fix_b;
+            if (need && rt >= 0 && rt < TROWS) {
+                const int sy = (gy < 0 ? -gy : 2 * (full_rows - 1) - gy) - ytop;
+                tile[rt * TWH + ct] = tile[sy * TWH + ct];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Cooperative reflect-indexed load: any size (iterated folding), any alignment, fp32 or u8 input.
+template <int R, int TWH, int TROWS, typename TIn>
+__device__ __forceinline__ void load_tile_manual(float* tile, const MarchArgs& a, int frame, int x0, int ytop,
+                                                 int nthreads)
+{
+    const char* base = (const char*)a.in + (long long)frame * a.in_frame_stride;
+    for (int i = threadIdx.x; i < TROWS * TWH; i += nthreads) {
+        const int rt = i / TWH, ct = i % TWH;
+        const int gy = dev::reflect101(ytop + rt, a.full_rows) - a.y_origin;
+        const int gx = dev::reflect101(x0 - march_halo_left(R) + ct, a.cols);
+        float v = 0.f;
+        if (gy >= 0 && gy < a.buf_rows) v = (float)((const TIn*)(base + (long long)gy * a.in_pitch))[gx];
+        tile[i] = v;
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// The marching kernel.  Fam supplies:
+//   R, NSETS, NROW, NBASIS, BH, MIN_CTAS
+//   row_set[NROW], row_odd[NROW]                  tap set / parity of each row-filtered plane
+//   basis_row[NBASIS], basis_set[NBASIS], basis_odd[NBASIS]   row plane / column tap set / parity per basis plane
+//   static void epilogue<MASK>(const float (&b)[NBASIS], const MarchArgs&, long long out_off, long long th_off)
+// ------------------------------------------------------------------------------------------------
+template <class Fam, unsigned MASK /* 0 = use a.mask at run time */, bool USE_TMA, typename TIn>
+__global__ void __launch_bounds__(MARCH_TW, Fam::MIN_CTAS)
+k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchArgs a,
+        const __grid_constant__ TapTable<Fam::NSETS, Fam::R> taps)
+{
+    constexpr int R = Fam::R, K = 2 * R + 1, TW = MARCH_TW, TWH = march_tile_width(R), BH = Fam::BH, TROWS = BH + 2 * R;
+    constexpr int NROW = Fam::NROW, NB = Fam::NBASIS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* tile = reinterpret_cast<float*>(smem_raw);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + sizeof(float) * TROWS * TWH);
+
+    const int frame = blockIdx.z;
+    const int x0 = blockIdx.x * TW;
+    const int yb = a.out_row_begin + blockIdx.y * BH;  // first image row this CTA produces
+    const int ytop = yb - R;                           // image row of tile row 0
+
+    if (USE_TMA) {
+        if (threadIdx.x == 0) {
+            ptx::prefetch_tmap(&tmap);
+            ptx::mbar_init(bar, 1);
+            ptx::fence_mbar_init();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            ptx::mbar_arrive_expect_tx(bar, TROWS * TWH * sizeof(float));
+            ptx::tma_load_3d(tile, &tmap, x0 - march_halo_left(R), ytop - a.y_origin, frame, bar);
+        }
+        ptx::mbar_wait(bar, 0);
+        patch_reflect<R, TWH, TROWS>(tile, x0, ytop, a.cols, a.full_rows, TW);
+    } else {
+        load_tile_manual<R, TWH, TROWS, TIn>(tile, a, frame, x0, ytop, TW);
+    }
+
+    const int x = x0 + threadIdx.x;
+    const bool xin = x < a.cols;
+    const float* tcol = tile + threadIdx.x + (march_halo_left(R) - R);  // leftmost tap of this thread's column
+    int nrows = a.out_row_end - yb;
+    nrows = nrows < BH ? nrows : BH;
+
+    float win[NROW][K];
+
+    // all unique row passes of one tile row -> slot `slot` of every window
+    auto row_pass = [&](int rt, auto slot_c) {
+        constexpr int slot = decltype(slot_c)::value;
+        const float* src = tcol + rt * TWH;
+        float v[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) v[k] = src[k];
+        float s[R + 1], d[R + 1];
+        s[0] = v[R];
+        d[0] = 0.f;
+#pragma unroll
+        for (int i = 1; i <= R; ++i) {
+            s[i] = v[R + i] + v[R - i];
+            d[i] = v[R + i] - v[R - i];
+        }
+#pragma unroll
+        for (int p = 0; p < NROW; ++p) {
+            const int set = Fam::row_set(p);
+            float acc;
+            if (Fam::row_odd(p)) {
+                acc = taps.t[set][1] * d[1];
+#pragma unroll
+                for (int i = 2; i <= R; ++i) acc = fmaf(taps.t[set][i], d[i], acc);
+            } else {
+                acc = taps.t[set][0] * s[0];
+#pragma unroll
+                for (int i = 1; i <= R; ++i) acc = fmaf(taps.t[set][i], s[i], acc);
+            }
+            win[p][slot] = acc;
+        }
+    };
+
+    // all column passes for the window whose newest row sits in `slot`, then the epilogue
+    auto col_pass_and_emit = [&](int y, auto slot_c) {
+        constexpr int slot = decltype(slot_c)::value;
+        constexpr int ctr = (slot + K - R) % K;  // slot of the centre row
+        float b[NB];
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+            const int rp = Fam::basis_row(q), set = Fam::basis_set(q);
+            float acc;
+            if (Fam::basis_odd(q)) {
+                acc = taps.t[set][1] * (win[rp][(ctr + 1) % K] - win[rp][(ctr + K - 1) % K]);
+#pragma unroll
+                for (int i = 2; i <= R; ++i)
+                    acc = fmaf(taps.t[set][i], win[rp][(ctr + i) % K] - win[rp][(ctr + K - i) % K], acc);
+            } else {
+                acc = taps.t[set][0] * win[rp][ctr];
+#pragma unroll
+                for (int i = 1; i <= R; ++i)
+                    acc = fmaf(taps.t[set][i], win[rp][(ctr + i) % K] + win[rp][(ctr + K - i) % K], acc);
+            }
+            b[q] = acc;
+        }
+        if (xin) {
+            const long long row_off = (long long)frame * a.out_frame_stride + (long long)(y - a.out_row_origin) * a.out_pitch;
+            Fam::template epilogue<MASK>(b, a, row_off, x);
+        }
+    };
+
+    // pre-roll: the first 2R tile rows only feed the window
+    {
+        auto pre = [&](auto rt_c) { row_pass(decltype(rt_c)::value, rt_c); };
+        [&]<int... I>(std::integer_sequence<int, I...>) { (pre(std::integral_constant<int, I>{}), ...); }
+        (std::make_integer_sequence<int, 2 * R>{});
+    }
+    // main loop, unrolled by K so that every window index is a compile-time constant (register rotation)
+#pragma unroll 1
+    for (int j = 0; j < nrows; j += K) {
+        auto step = [&](auto ph_c) {
+            constexpr int ph = decltype(ph_c)::value;
+            constexpr int slot = (2 * R + ph) % K;
+            if (j + ph < nrows) {
+                row_pass(2 * R + j + ph, std::integral_constant<int, slot>{});
+                col_pass_and_emit(yb + j + ph, std::integral_constant<int, slot>{});
+            }
+        };
+        [&]<int... I>(std::integer_sequence<int, I...>) { (step(std::integral_constant<int, I>{}), ...); }
+        (std::make_integer_sequence<int, K>{});
+    }
+}
+
+}  // namespace cvs

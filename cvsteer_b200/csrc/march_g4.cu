@@ -1,0 +1,17 @@
+// G4/H4 instantiations of the marching kernel (reference cvsteer/SteerableFiltersG4.cpp:67-122 fused).
+#include "march_launch.cuh"
+
+namespace cvs {
+
+cudaError_t launch_march_g4(const FamilyTaps& taps, const BatchGeom& g, const MarchArgs& a, bool dom, cudaStream_t stream, LaunchInfo* info)
+{
+    // the reference has no G4 orientation analysis (G4.h:40-41,55): there is no dominant angle to steer to
+    if (dom && (a.mask & G4Fam::kNeedsSteer)) return cudaErrorInvalidValue;
+    TapTable<G4Fam::NSETS, G4Fam::R> tt;
+    fill_tap_table<G4Fam>(taps, tt);
+    const int out_rows = g.out_row_end - g.out_row_begin;
+    const dim3 grid((g.cols + MARCH_TW - 1) / MARCH_TW, (out_rows + G4Fam::BH - 1) / G4Fam::BH, g.n);
+    return launch_march_mask<G4Fam, 0u>(g, a, tt, grid, stream, info, "g4_march<dyn>");
+}
+
+}  // namespace cvs

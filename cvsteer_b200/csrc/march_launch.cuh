@@ -1,0 +1,151 @@
+// Host-side launch helpers for the marching kernel (tensor-map creation, variant selection).
+// Included by march_g2.cu / march_g4.cu (one translation unit per family so they compile in parallel).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "families.cuh"
+#include "launch.h"
+
+namespace cvs {
+
+extern std::atomic<unsigned long long> g_launches;
+
+// ------------------------------------------------------------------------------------------------
+// TMA tensor map (driver entry point fetched through the runtime: no link-time libcuda dependency)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static inline PFN_encodeTiled get_encode_fn()
+{
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    });
+    return fn;
+}
+
+// 3-D fp32 tensor (x = cols, y = buffer rows, z = frames); box = (box_w, box_h, 1); OOB -> zeros.
+static inline bool make_tmap(CUtensorMap* m, const BatchGeom& g, int box_w, int box_h)
+{
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)g.cols, (cuuint64_t)g.buf_rows, (cuuint64_t)g.n};
+    cuuint64_t strides[2] = {(cuuint64_t)g.in_pitch, (cuuint64_t)(g.n > 1 ? g.in_frame_stride : g.in_pitch * (size_t)g.buf_rows)};
+    cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(g.in), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+static inline bool tma_eligible(const BatchGeom& g, int R)
+{
+    static const bool force_ldg = getenv("CVS_FORCE_LDG") != nullptr;  // A/B switch for profiling the two loaders
+    if (force_ldg) return false;
+    if (g.in_u8) return false;
+    if (((uintptr_t)g.in & 15) || (g.in_pitch & 15) || (g.in_frame_stride & 15)) return false;
+    if (g.cols < R + 1 || g.full_rows < R + 1) return false;  // one reflect fold must land inside the tile
+    if (g.n > 1 && g.in_frame_stride < g.in_pitch * (size_t)g.buf_rows) return false;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Marching-kernel dispatch
+// ------------------------------------------------------------------------------------------------
+template <class Fam>
+static void fill_tap_table(const FamilyTaps& ft, TapTable<Fam::NSETS, Fam::R>& tt)
+{
+    for (int api = 0; api < ft.nsets; ++api) {
+        const int u = Fam::unique_of(api);
+        for (int i = 0; i <= Fam::R; ++i) tt.t[u][i] = ft.t[api][Fam::R + i];
+    }
+}
+
+template <class Fam, unsigned MASK, bool TMA, typename TIn>
+static cudaError_t launch_march_one(const CUtensorMap& tm, const MarchArgs& a, const TapTable<Fam::NSETS, Fam::R>& tt, dim3 grid,
+                                    cudaStream_t stream, LaunchInfo* info, const char* name)
+{
+    constexpr int TROWS = Fam::BH + 2 * Fam::R, TWH = march_tile_width(Fam::R);
+    constexpr int smem = TROWS * TWH * (int)sizeof(float) + 16;
+    auto kfn = k_march<Fam, MASK, TMA, TIn>;
+    static std::once_flag once;  // one per instantiation
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [&] {
+        attr_err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    });
+    if (attr_err != cudaSuccess) return attr_err;
+    kfn<<<grid, MARCH_TW, smem, stream>>>(tm, a, tt);
+    g_launches.fetch_add(1);
+    if (info) {
+        info->grid[0] = grid.x, info->grid[1] = grid.y, info->grid[2] = grid.z;
+        info->block = MARCH_TW;
+        info->smem = smem;
+        snprintf(info->name, sizeof(info->name), "%s", name);
+    }
+    return cudaGetLastError();
+}
+
+template <class Fam, unsigned MASK>
+static cudaError_t launch_march_mask(const BatchGeom& g, const MarchArgs& a, const TapTable<Fam::NSETS, Fam::R>& tt, dim3 grid,
+                                     cudaStream_t stream, LaunchInfo* info, const char* name)
+{
+    CUtensorMap tm;
+    memset(&tm, 0, sizeof(tm));
+    constexpr int TROWS = Fam::BH + 2 * Fam::R, TWH = march_tile_width(Fam::R);
+    char nm[96];
+    if (tma_eligible(g, Fam::R) && make_tmap(&tm, g, TWH, TROWS)) {
+        snprintf(nm, sizeof(nm), "%s/tma", name);
+        return launch_march_one<Fam, MASK, true, float>(tm, a, tt, grid, stream, info, nm);
+    }
+    if (g.in_u8) {
+        snprintf(nm, sizeof(nm), "%s/ldg-u8", name);
+        return launch_march_one<Fam, MASK, false, unsigned char>(tm, a, tt, grid, stream, info, nm);
+    }
+    snprintf(nm, sizeof(nm), "%s/ldg", name);
+    return launch_march_one<Fam, MASK, false, float>(tm, a, tt, grid, stream, info, nm);
+}
+
+static inline MarchArgs make_args(const BatchGeom& g, unsigned mask, const SteerSpec& st, float* const* outs, int nplanes)
+{
+    MarchArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in = g.in;
+    a.in_pitch = (long long)g.in_pitch;
+    a.in_frame_stride = (long long)g.in_frame_stride;
+    a.cols = g.cols;
+    a.full_rows = g.full_rows;
+    a.buf_rows = g.buf_rows;
+    a.y_origin = g.y_origin;
+    a.out_row_begin = g.out_row_begin;
+    a.out_row_end = g.out_row_end;
+    a.out_row_origin = g.out_row_origin;
+    a.out_pitch = (long long)g.out_pitch;
+    a.out_frame_stride = (long long)g.out_frame_stride;
+    a.mask = mask;
+    a.steer_source = st.source;
+    a.cos_t = st.cos_t;
+    a.sin_t = st.sin_t;
+    a.theta_map = st.theta_map;
+    for (int p = 0; p < nplanes && p < MARCH_MAX_OUT; ++p) a.out[p] = (mask >> p & 1u) ? outs[p] : nullptr;
+    return a;
+}
+
+
+}  // namespace cvs

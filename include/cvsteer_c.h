@@ -1,0 +1,209 @@
+/*
+ * cvsteer_c.h -- C ABI of libcvsteer_b200.so: the B200 (sm_100a) implementation of cvsteer's hot path.
+ *
+ * This is the drop-in boundary.  Plain pointers and sizes only; no C++/torch/OpenCV types.  Every entry
+ * point cites the reference interface it replaces (paths relative to the reference tree,
+ * headupinclouds/cvsteer).  The C++ classes in include/cvsteer/SteerableFiltersG{2,4}.h keep the
+ * reference's class surface and forward here; INTEGRATION.md shows the binding a maintainer adds.
+ *
+ * Conventions
+ *   - All images are single-channel fp32, row-major; `step`/`pitch` arguments are BYTES per row
+ *     (cv::Mat::step), `rows`/`cols` as in cv::Mat.
+ *   - Every function returns 0 on success or a negative cvs_status; cvs_last_error() gives text for the
+ *     calling thread.  Nothing throws across this boundary.  There is NO CPU fallback: without a CUDA
+ *     device every compute entry point fails with CVS_ERR_CUDA.
+ *   - A handle is single-threaded; distinct handles may be used concurrently from different threads
+ *     (each owns its stream), mirroring the reference where each cv::parallel_for_ iteration builds
+ *     its own filter object (example/steer.cpp:69-90,169).
+ *   - The library never allocates caller memory: outputs are caller-provided (wrapper does Mat::create).
+ */
+#ifndef CVSTEER_C_H_
+#define CVSTEER_C_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define CVS_API __declspec(dllexport)
+#else
+#define CVS_API __attribute__((visibility("default")))
+#endif
+
+typedef enum cvs_status {
+    CVS_OK = 0,
+    CVS_ERR_INVALID_ARG = -1,   /* null pointer, rows/cols <= 0, width out of range, step < cols*4 ... */
+    CVS_ERR_CUDA = -2,          /* any CUDA runtime/driver failure (incl. no device) */
+    CVS_ERR_NOT_SETUP = -3,     /* steer/get before setup (reference: empty Mats -> cv::Exception) */
+    CVS_ERR_SIZE_MISMATCH = -4, /* theta map / input planes not the size of the set-up image */
+    CVS_ERR_UNSUPPORTED = -5
+} cvs_status;
+
+/* Output planes.  Bit i of a `mask` selects plane i.  Names follow the reference's members
+ * (cvsteer/SteerableFiltersG2.h:62-66) and steer() outputs (SteerableFiltersG2.cpp:157-177). */
+typedef enum cvs_g2_plane {
+    CVS_G2A = 0, CVS_G2B, CVS_G2C, CVS_H2A, CVS_H2B, CVS_H2C, CVS_H2D, /* 7 basis planes  G2.cpp:62-68 */
+    CVS_C1 = 7, CVS_C2, CVS_C3,                                         /* G2.cpp:93-95 */
+    CVS_THETA = 10,      /* dominant orientation angle, (-pi/2, pi/2]      G2.cpp:97-99 */
+    CVS_STRENGTH = 11,   /* dominant orientation strength sqrt(c2^2+c3^2)  G2.cpp:97 */
+    CVS_G2T = 12,        /* G2 steered to the chosen angle                 G2.cpp:153 */
+    CVS_H2T = 13,        /* H2 steered                                     G2.cpp:154 */
+    CVS_E = 14,          /* oriented energy c1 + c2 cos2t + c3 sin2t       G2.cpp:174-176 */
+    CVS_MAG = 15,        /* sqrt(g2^2+h2^2)                                G2.cpp:109 */
+    CVS_PHASE = 16,      /* wrap(atan2(h2,g2)) in (-pi,pi], NaN->0         G2.cpp:109-111 */
+    CVS_EDGES = 17,      /* findEdges(magnitude, phase)      G2.cpp:201-204, fed as callers do */
+    CVS_DARK = 18,       /* findDarkLines(magnitude, phase)  G2.cpp:205-208 */
+    CVS_BRIGHT = 19,     /* findBrightLines(magnitude,phase) G2.cpp:209-212 */
+    CVS_G2_NPLANES = 20
+} cvs_g2_plane;
+
+#define CVS_BIT(p) (1u << (p))
+/* M0: the class state setup() leaves behind (7 basis + c1..c3 + theta + strength) */
+#define CVS_G2_MASK_STATE 0x00000FFFu
+/* M1: orientation analysis only: theta_d, strength, energy at theta_d */
+#define CVS_G2_MASK_ORIENT (CVS_BIT(CVS_THETA) | CVS_BIT(CVS_STRENGTH) | CVS_BIT(CVS_E))
+/* M2: full fused basis+steer+orientation: theta_d, strength, g2, h2, e, magnitude, phase */
+#define CVS_G2_MASK_FULL (CVS_G2_MASK_ORIENT | CVS_BIT(CVS_G2T) | CVS_BIT(CVS_H2T) | CVS_BIT(CVS_MAG) | CVS_BIT(CVS_PHASE))
+
+typedef enum cvs_g4_plane {
+    CVS_G4A = 0, CVS_G4B, CVS_G4C, CVS_G4D, CVS_G4E,                /* G4.cpp:69-73 */
+    CVS_H4A = 5, CVS_H4B, CVS_H4C, CVS_H4D, CVS_H4E, CVS_H4F,        /* G4.cpp:75-80 */
+    CVS_G4T = 11,      /* G4 steered  G4.cpp:110 / :120 */
+    CVS_H4T = 12,      /* H4 steered  G4.cpp:111 / :121 */
+    CVS_MAG4 = 13,     /* sqrt(g4^2+h4^2): the reference's G4 computeMagnitudeAndPhase is empty */
+    CVS_PHASE4 = 14,   /* (G4.cpp:88-90); defined as the G2 class's (G2.cpp:107-112) on (g4,h4) */
+    CVS_G4_NPLANES = 15
+} cvs_g4_plane;
+#define CVS_G4_MASK_BASIS 0x000007FFu
+#define CVS_G4_MASK_STEER (CVS_BIT(CVS_G4T) | CVS_BIT(CVS_H4T) | CVS_BIT(CVS_MAG4) | CVS_BIT(CVS_PHASE4))
+
+/* Which angle the fused kernels steer to. */
+typedef enum cvs_steer_source {
+    CVS_STEER_DOMINANT = 0, /* per-pixel theta_d computed in the same kernel (what both reference callers do:
+                               example/steer.cpp:87, test/test.cpp:86).  G2 only. */
+    CVS_STEER_SCALAR = 1,   /* one angle for the image   steer(float theta, ...)  G2.cpp:137, G4.cpp:114 */
+    CVS_STEER_MAP = 2       /* per-pixel angle map       steer(const Mat1f& theta, ...) G2.cpp:147, G4.cpp:92 */
+} cvs_steer_source;
+
+typedef struct cvs_g2 cvs_g2;   /* replaces fa::SteerableFiltersG2  (cvsteer/SteerableFiltersG2.h:35) */
+typedef struct cvs_g4 cvs_g4;   /* replaces fa::SteerableFiltersG4  (cvsteer/SteerableFiltersG4.h:35) */
+
+CVS_API const char* cvs_version(void);
+CVS_API const char* cvs_last_error(void);     /* thread-local text of the last failure */
+CVS_API int cvs_device_count(int* count);
+
+/* ---- taps: SteerableFilters::create (cvsteer/SteerableFilters.cpp:33-42) with the reference's tap
+ *      functions G21..G23,H21..H24 (G2.cpp:35-42) / G41..G45,H41..H46 (G4.cpp:34-45).  Host-only.
+ *      `which`: G2 family 0..6 = g1,g2,g3,h1,h2,h3,h4;  G4 family 0..10 = g1..g5,h1..h6.
+ *      Writes 2*width+1 floats. */
+CVS_API int cvs_g2_make_taps(int which, int width, float spacing, float* dst);
+CVS_API int cvs_g4_make_taps(int which, int width, float spacing, float* dst);
+
+/* ================================ G2/H2 handle (class semantics) ================================ */
+/* ctor part 1 (taps) -- SteerableFiltersG2::SteerableFiltersG2 G2.cpp:44-56.  1 <= width <= 32. */
+CVS_API int cvs_g2_create(cvs_g2** out, int device, int width, float spacing);
+CVS_API int cvs_g2_destroy(cvs_g2* h);
+/* setup(const Mat1f&) G2.cpp:60-100: upload, fused basis + C1..C3 + theta_d + strength, results stay
+ * resident on the device.  Re-callable (re-uses taps), any size >= 1x1. */
+CVS_API int cvs_g2_setup_host(cvs_g2* h, const float* image, int rows, int cols, size_t step);
+/* same, from 8-bit gray (what both callers pass: the implicit Mat(8UC1)->Mat1f conversion of
+ * example/steer.cpp:86 / test/test.cpp:85 is done on the device; values 0..255, no scaling). */
+CVS_API int cvs_g2_setup_host_u8(cvs_g2* h, const uint8_t* image, int rows, int cols, size_t step);
+CVS_API int cvs_g2_size(const cvs_g2* h, int* rows, int* cols);
+/* protected members / getters (G2.h:40-41,62-66): download one plane of the class state
+ * (CVS_G2A..CVS_STRENGTH). */
+CVS_API int cvs_g2_get_plane_host(cvs_g2* h, int plane, float* dst, size_t step);
+/* steer(float theta, g2,h2[,e,magnitude,phase]) G2.cpp:137-145,157-165.  Any output may be NULL. */
+CVS_API int cvs_g2_steer_scalar_host(cvs_g2* h, float theta, float* g2, float* h2, float* e,
+                                     float* magnitude, float* phase, size_t step);
+/* steer(const Mat1f& theta, g2,h2[,e,magnitude,phase]) G2.cpp:147-155,167-177.
+ * theta == NULL means "the handle's own dominant-orientation map" without a host round trip
+ * (the callers' steer(getDominantOrientationAngle(), ...) idiom). */
+CVS_API int cvs_g2_steer_map_host(cvs_g2* h, const float* theta, size_t theta_step, float* g2, float* h2,
+                                  float* e, float* magnitude, float* phase, size_t step);
+/* steer(const Point&, float, ...) G2.cpp:115-134: out = {g2, h2, e, magnitude, phase}; phase here is the
+ * reference's plain atan2 (no wrap, no NaN patch), as in G2.cpp:128. */
+CVS_API int cvs_g2_steer_point(cvs_g2* h, int x, int y, float theta, float out[5]);
+
+/* ---- stateless point-wise ops on host images (static / non-member-like in the reference) ---- */
+/* computeMagnitudeAndPhase G2.cpp:107-112 */
+CVS_API int cvs_magnitude_phase_host(int device, const float* g, const float* h, size_t in_step,
+                                     float* magnitude, float* phase, size_t out_step, int rows, int cols);
+/* phaseWeights G2.cpp:179-186 (k unused in the reference; accepted and ignored) */
+CVS_API int cvs_phase_weights_host(int device, const float* phase, size_t in_step, float* lambda,
+                                   size_t out_step, int rows, int cols, float phi, int signum, float k);
+/* findEdges / findDarkLines / findBrightLines G2.cpp:201-212: kind = 0 edges, 1 dark, 2 bright */
+CVS_API int cvs_find_host(int device, int kind, const float* e, const float* phase, size_t in_step,
+                          float* out, size_t out_step, int rows, int cols, float k);
+
+/* ================================ G4/H4 handle ================================ */
+CVS_API int cvs_g4_create(cvs_g4** out, int device, int width, float spacing);   /* G4.cpp:47-65 */
+CVS_API int cvs_g4_destroy(cvs_g4* h);
+CVS_API int cvs_g4_setup_host(cvs_g4* h, const float* image, int rows, int cols, size_t step); /* G4.cpp:67-81 */
+CVS_API int cvs_g4_size(const cvs_g4* h, int* rows, int* cols);
+CVS_API int cvs_g4_get_plane_host(cvs_g4* h, int plane, float* dst, size_t step);  /* CVS_G4A..CVS_H4F */
+/* steer(float theta, g4, h4) G4.cpp:114-122; magnitude/phase optional (see CVS_MAG4) */
+CVS_API int cvs_g4_steer_scalar_host(cvs_g4* h, float theta, float* g4, float* h4, float* magnitude,
+                                     float* phase, size_t step);
+/* steer(const Mat1f& theta, g4, h4) G4.cpp:92-112 */
+CVS_API int cvs_g4_steer_map_host(cvs_g4* h, const float* theta, size_t theta_step, float* g4, float* h4,
+                                  float* magnitude, float* phase, size_t step);
+
+/* ================================ device-resident batch path ================================
+ * The throughput path: frames already in HBM, outputs written to HBM, one fused launch per pyramid
+ * level, nothing else touches memory.  The reference has no batch API; this is its per-file loop
+ * (example/steer.cpp:69-124) with the file I/O removed.
+ *
+ * A batch is `n` frames of rows x cols, frame f at  base + f*frame_stride  bytes, row r at + r*pitch.
+ * outs[p] (device pointer, same n/pitch/frame_stride convention via out_pitch/out_frame_stride) is
+ * written for every p set in `mask`; other entries are ignored and may be NULL.
+ * `stream` is a cudaStream_t (0 = default stream); the call is asynchronous on it.
+ */
+typedef struct cvs_batch {
+    const void* in;          /* device pointer: fp32, or u8 when in_is_u8 != 0 */
+    int in_is_u8;
+    int n, rows, cols;
+    size_t in_pitch, in_frame_stride;
+    size_t out_pitch, out_frame_stride;
+    /* Row-band support (one huge image split across GPUs): the buffer holds image
+     * rows [y_origin, y_origin+rows) of an image that is `full_rows` tall; outputs are produced for
+     * image rows [out_row_begin, out_row_end) only and written at buffer-relative row
+     * (y - out_row_origin) of the output planes.  Vertical reflect-101 applies at image rows <0 and
+     * >= full_rows only.  For whole frames set full_rows = 0 (=> y_origin 0, all rows). */
+    int full_rows, y_origin, out_row_begin, out_row_end, out_row_origin;
+} cvs_batch;
+
+CVS_API int cvs_g2_run_batch_dev(cvs_g2* h, const cvs_batch* b, unsigned mask, int steer_source,
+                                 float theta_scalar, const float* theta_map /* device, out_pitch layout */,
+                                 float* const* outs, void* stream);
+CVS_API int cvs_g4_run_batch_dev(cvs_g4* h, const cvs_batch* b, unsigned mask, int steer_source,
+                                 float theta_scalar, const float* theta_map, float* const* outs, void* stream);
+
+/* Pyramid level l -> l+1 on the device.  No reference counterpart; defined as cv::pyrDown:
+ * [1 4 6 4 1]^2/256, BORDER_REFLECT_101, even samples, out size ((cols+1)/2, (rows+1)/2).
+ * Band fields of `b` apply to the INPUT level; outputs rows [out_row_begin,out_row_end) are in the
+ * coordinates of the OUTPUT level. */
+CVS_API int cvs_pyr_down_dev(int device, const cvs_batch* b, float* out, void* stream);
+
+/* Host-buffer batch (the end-to-end call a user with frames in host memory makes): uploads in chunks,
+ * runs the fused kernel, downloads the selected planes; copies and kernels overlap on internal
+ * streams.  Host buffers should be pinned for full PCIe rate.  steer source = dominant. */
+CVS_API int cvs_g2_run_batch_host(cvs_g2* h, const float* in, int n, int rows, int cols, size_t in_step,
+                                  size_t in_frame_stride, unsigned mask, float* const* outs,
+                                  size_t out_step, size_t out_frame_stride);
+
+/* ---- measurement helpers (used by bench.py; not part of the reference surface) ---- */
+/* Saturating FFMA loop: returns achieved fp32 instructions/s (1 FFMA = 1 instr = 2 flop).
+ * form: 0 = immediate-operand FFMA, 1 = register-operand, 2 = constant-bank operand. */
+CVS_API int cvs_bench_ffma(int device, int form, int iters, double* instr_per_s, float* elapsed_ms);
+/* Last kernel launch configuration of a handle, for reporting (grid, block, dynamic smem bytes, kernel name). */
+CVS_API int cvs_g2_last_launch(const cvs_g2* h, int* grid_xyz, int* block, int* smem, char* name, int name_len);
+CVS_API unsigned long long cvs_launch_count(void);  /* kernels launched by this library so far (process-wide) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CVSTEER_C_H_ */

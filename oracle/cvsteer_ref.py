@@ -45,7 +45,9 @@ F32 = np.float32
 # --------------------------------------------------------------------------------------
 def _expf_neg_sq(x: np.float32) -> float:
     xx = F32(x) * F32(x)  # float * float
-    return float(F32(np.exp(F32(-xx))))  # expf
+    # expf: glibc's expf is correctly rounded in practice; numpy's SIMD float32 exp is not always,
+    # so round the double result instead of calling np.exp on a float32.
+    return float(F32(math.exp(float(F32(-xx)))))
 
 
 def _f(v: float) -> np.float32:
@@ -56,10 +58,12 @@ def _f(v: float) -> np.float32:
 def G21(x): xd = float(x); return _f(0.9213 * (2.0 * xd * xd - 1.0) * _expf_neg_sq(x))
 def G22(x): return _f(_expf_neg_sq(x))
 def G23(x): xd = float(x); return _f(math.sqrt(1.8430) * xd * _expf_neg_sq(x))
-def H21(x): xd = float(x); return _f(0.9780 * (-2.254 * xd + xd * xd * xd) * _expf_neg_sq(x))
+def H21(x):  # `x * x * x` is a float product in C++; `-2.254 * x` is double
+    xf = F32(x)
+    return _f(0.9780 * (-2.254 * float(xf) + float(xf * xf * xf)) * _expf_neg_sq(x))
 def H22(x): return _f(_expf_neg_sq(x))
 def H23(x): return _f(float(F32(x) * F32(_expf_neg_sq(x))))  # float * float
-def H24(x): xd = float(x); return _f(0.9780 * (-0.7515 + xd * xd) * _expf_neg_sq(x))
+def H24(x): xf = F32(x); return _f(0.9780 * (-0.7515 + float(xf * xf)) * _expf_neg_sq(x))
 
 
 # cvsteer/SteerableFiltersG4.cpp:34-45.  Note `3.0f * x * x` is float arithmetic that is
@@ -80,15 +84,16 @@ def G45(x):
     return _f(math.sqrt(1.246) * (float(xf * xf) - 0.5) * _expf_neg_sq(x))
 def H41(x):
     xf = F32(x)
-    x3 = float(xf * xf * xf)
-    x5 = float(xf * xf * xf * xf * xf)
-    return _f(0.3975 * (7.189 * float(xf) - 7.501 * x3 + x5) * _expf_neg_sq(x))
+    xd = float(xf)
+    x5 = float(xf * xf * xf * xf * xf)           # float product
+    # `7.501 * x * x * x` associates as ((7.501*x)*x)*x: all double
+    return _f(0.3975 * (7.189 * xd - 7.501 * xd * xd * xd + x5) * _expf_neg_sq(x))
 def H42(x): return _f(_expf_neg_sq(x))
 def H43(x):
     xf = F32(x)
-    x2 = float(xf * xf)
-    x4 = float(xf * xf * xf * xf)
-    return _f(0.3975 * (1.438 - 4.501 * x2 + x4) * _expf_neg_sq(x))
+    xd = float(xf)
+    x4 = float(xf * xf * xf * xf)                # float product
+    return _f(0.3975 * (1.438 - 4.501 * xd * xd + x4) * _expf_neg_sq(x))  # (4.501*x)*x in double
 def H44(x): return _f(float(F32(x) * F32(_expf_neg_sq(x))))
 def H45(x):
     xf = F32(x)

@@ -1,0 +1,79 @@
+"""CPU-only checks of the drop-in boundary: the library loads, exports every symbol include/cvsteer_c.h
+declares, generates the reference's taps, and fails loudly (never falls back) without a device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    txt = open(os.path.join(ROOT, "include", "cvsteer_c.h")).read()
+    return sorted(set(re.findall(r"CVS_API\s+[\w\s\*]+?\b(cvs_\w+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    from cvsteer_b200 import capi
+    lib = capi.lib()
+    syms = _header_symbols()
+    assert len(syms) >= 30
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in cvsteer_c.h but not exported"
+    assert sorted(capi.EXPORTED_SYMBOLS) == syms, "ctypes binding and header disagree"
+    assert b"sm_100a" in lib.cvs_version()
+
+
+def test_enum_values_match_header():
+    from cvsteer_b200 import capi
+    txt = open(os.path.join(ROOT, "include", "cvsteer_c.h")).read()
+    assert "CVS_C1 = 7" in txt and "CVS_THETA = 10" in txt and "CVS_G2T = 12" in txt and "CVS_EDGES = 17" in txt
+    assert capi.C1 == 7 and capi.THETA == 10 and capi.G2T == 12 and capi.EDGES == 17 and capi.G2_NPLANES == 20
+    assert "CVS_H4A = 5" in txt and "CVS_G4T = 11" in txt and capi.H4A == 5 and capi.G4T == 11
+    assert capi.G2_MASK_ORIENT == 0x4C00 and capi.G2_MASK_FULL == 0x1FC00
+
+
+def test_host_taps_equal_oracle_taps(taps_default):
+    import cvsteer_b200 as cb
+    for i, n in enumerate(("g1", "g2", "g3", "h1", "h2", "h3", "h4")):
+        assert np.array_equal(cb.make_taps_g2(i), taps_default[n]), n
+    for i, n in enumerate(("g1", "g2", "g3", "g4", "g5", "h1", "h2", "h3", "h4", "h5", "h6")):
+        assert np.array_equal(cb.make_taps_g4(i), taps_default["G4_" + n]), n
+
+
+def test_host_taps_other_widths_equal_oracle():
+    import cvsteer_b200 as cb
+    from oracle import cvsteer_ref as ref
+    g2 = (ref.G21, ref.G22, ref.G23, ref.H21, ref.H22, ref.H23, ref.H24)
+    g4 = (ref.G41, ref.G42, ref.G43, ref.G44, ref.G45, ref.H41, ref.H42, ref.H43, ref.H44, ref.H45, ref.H46)
+    for w, s in ((3, 0.8), (9, 0.31), (1, 1.0), (32, 0.1)):
+        for i, fn in enumerate(g2):
+            assert np.array_equal(cb.make_taps_g2(i, w, s), ref.create(w, s, fn)[0]), (w, s, i)
+        for i, fn in enumerate(g4):
+            assert np.array_equal(cb.make_taps_g4(i, w, s), ref.create(w, s, fn)[0]), (w, s, i)
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    import cvsteer_b200 as cb
+    from cvsteer_b200 import capi
+    with pytest.raises(capi.CvsError) as e:
+        cb.SteerableFiltersG2(np.zeros((8, 8), np.float32))
+    assert e.value.code == capi.ERR_CUDA
+    n = C.c_int(-1)
+    assert capi.lib().cvs_device_count(C.byref(n)) == capi.ERR_CUDA
+
+
+def test_product_code_never_imports_oracle():
+    """The shipped package must not reference oracle/ (or cv2) anywhere."""
+    pkg = os.path.join(ROOT, "cvsteer_b200")
+    for dp, _, fns in os.walk(pkg):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dp, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), fn
+                assert "import cv2" not in src, fn

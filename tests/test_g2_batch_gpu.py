@@ -1,0 +1,189 @@
+"""Device-resident fused batch path (cvs_g2_run_batch_dev) vs the oracle, plus structural properties."""
+import numpy as np
+import pytest
+import torch
+
+from cvsteer_b200 import capi
+from cvsteer_b200.batch import Band, G2Batch, pyr_down
+from oracle import cvsteer_ref as ref
+from tests.util import assert_angle_close, assert_close_range, basis_range, synth
+
+pytestmark = pytest.mark.gpu
+STATE = ("g2a", "g2b", "g2c", "h2a", "h2b", "h2c", "h2d")
+
+
+def _frames(seed0, n, rows, cols):
+    return np.stack([synth(seed0 + i, rows, cols) for i in range(n)])
+
+
+def _check_full(res, i, o, rng, tag=""):
+    th = res["theta"][i].cpu().numpy()
+    assert_angle_close(th, o.theta, o.strength, np.pi, tag + "theta")
+    assert_close_range(res["strength"][i].cpu().numpy(), o.strength, rng * rng, tag + "strength")
+    w = o.steer_map_full(th)
+    assert_close_range(res["g2"][i].cpu().numpy(), w[0], rng, tag + "g2")
+    assert_close_range(res["h2"][i].cpu().numpy(), w[1], rng, tag + "h2")
+    assert_close_range(res["e"][i].cpu().numpy(), w[2], rng * rng, tag + "e")
+    assert_close_range(res["magnitude"][i].cpu().numpy(), w[3], rng, tag + "magnitude")
+    assert_angle_close(res["phase"][i].cpu().numpy(), w[4], w[3], 2 * np.pi, tag + "phase")
+
+
+@pytest.mark.parametrize("shape", [(72, 256), (130, 131), (200, 520), (64, 128), (1080, 1920)])
+def test_modes_vs_oracle(shape):
+    n = 3 if shape[0] < 1000 else 1
+    fr = _frames(3000, n, *shape)
+    x = torch.from_numpy(fr).cuda()
+    g = G2Batch()
+    m0 = g.run(x, capi.G2_MASK_STATE)
+    m1 = g.run(x, capi.G2_MASK_ORIENT)
+    m2 = g.run(x, capi.G2_MASK_FULL)
+    assert "tma" in g.last_launch()["kernel"] or shape[1] % 4
+    for i in range(n):
+        o = ref.SteerableFiltersG2(fr[i])
+        rng = basis_range([getattr(o, k) for k in STATE])
+        for k in STATE:
+            assert_close_range(m0[k][i].cpu().numpy(), getattr(o, k), rng, f"M0 {k}")
+        for k in ("c1", "c2", "c3", "strength"):
+            assert_close_range(m0[k][i].cpu().numpy(), getattr(o, k), rng * rng, f"M0 {k}")
+        assert_angle_close(m0["theta"][i].cpu().numpy(), o.theta, o.strength, np.pi, "M0 theta")
+        # M1: energy at theta_d  (oracle: c1 + c2 cos 2t + c3 sin 2t at t = theta_d)
+        _, _, e1 = ref.g2_orientation(fr[i])
+        assert_close_range(m1["e"][i].cpu().numpy(), e1, rng * rng, "M1 e")
+        assert torch.equal(m1["theta"][i], m0["theta"][i]) and torch.equal(m1["strength"][i], m0["strength"][i])
+        _check_full(m2, i, o, rng, "M2 ")
+        assert torch.equal(m2["theta"][i], m0["theta"][i])
+
+
+def test_all_planes_dynamic_mask_and_find_maps():
+    fr = _frames(3100, 2, 96, 200)
+    x = torch.from_numpy(fr).cuda()
+    g = G2Batch()
+    mask = (1 << capi.G2_NPLANES) - 1
+    r = g.run(x, mask)
+    for i in range(2):
+        o = ref.SteerableFiltersG2(fr[i])
+        rng = basis_range([getattr(o, k) for k in STATE])
+        _check_full(r, i, o, rng, "dyn ")
+        mag, ph = r["magnitude"][i].cpu().numpy(), r["phase"][i].cpu().numpy()
+        for k, fn in (("edges", ref.find_edges), ("lines_dark", ref.find_dark_lines), ("lines_bright", ref.find_bright_lines)):
+            assert_close_range(r[k][i].cpu().numpy(), fn(mag, ph), rng, k)
+
+
+def test_scalar_and_map_steering_fused():
+    fr = _frames(3200, 1, 80, 150)
+    x = torch.from_numpy(fr).cuda()
+    g = G2Batch()
+    o = ref.SteerableFiltersG2(fr[0])
+    rng = basis_range([getattr(o, k) for k in STATE])
+    mask = capi.bit(capi.G2T) | capi.bit(capi.H2T) | capi.bit(capi.E) | capi.bit(capi.MAG) | capi.bit(capi.PHASE)
+    r = g.run(x, mask, steer=capi.STEER_SCALAR, theta=0.7)
+    w = o.steer_scalar_full(0.7)
+    for k, j, s in (("g2", 0, rng), ("h2", 1, rng), ("e", 2, rng * rng), ("magnitude", 3, rng)):
+        assert_close_range(r[k][0].cpu().numpy(), w[j], s, "scalar " + k)
+    th = np.random.default_rng(9).uniform(-4, 4, (1, 80, 150)).astype(np.float32)
+    r = g.run(x, mask, steer=capi.STEER_MAP, theta_map=torch.from_numpy(th).cuda())
+    w = o.steer_map_full(th[0])
+    for k, j, s in (("g2", 0, rng), ("h2", 1, rng), ("e", 2, rng * rng), ("magnitude", 3, rng)):
+        assert_close_range(r[k][0].cpu().numpy(), w[j], s, "map " + k)
+    assert_angle_close(r["phase"][0].cpu().numpy(), w[4], w[3], 2 * np.pi, "map phase")
+
+
+def test_tma_and_ldg_loaders_agree_bitwise():
+    """Same pixels through the TMA-staged tile and through the cooperative reflect-indexed loader."""
+    fr = _frames(3300, 2, 150, 260)
+    g = G2Batch()
+    x = torch.from_numpy(fr).cuda()
+    a = g.run(x, capi.G2_MASK_STATE)
+    assert g.last_launch()["kernel"].endswith("/tma")
+    pad = torch.zeros((2, 150, 263), dtype=torch.float32, device="cuda")
+    pad[:, :, 1:261] = x
+    b = g.run(pad[:, :, 1:261], capi.G2_MASK_STATE)   # misaligned base + pitch: TMA cannot describe it
+    assert g.last_launch()["kernel"].endswith("/ldg")
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_u8_input_matches_float_input():
+    img8 = np.random.default_rng(4).integers(0, 256, (2, 100, 300), dtype=np.uint8)
+    g = G2Batch()
+    a = g.run(torch.from_numpy(img8).cuda(), capi.G2_MASK_FULL)
+    assert "u8" in g.last_launch()["kernel"]
+    b = g.run(torch.from_numpy(img8.astype(np.float32)).cuda(), capi.G2_MASK_FULL)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_frame_independence_and_batch_consistency():
+    fr = _frames(3400, 5, 70, 140)
+    g = G2Batch()
+    full = g.run(torch.from_numpy(fr).cuda(), capi.G2_MASK_FULL)
+    one = g.run(torch.from_numpy(fr[3:4]).cuda(), capi.G2_MASK_FULL)
+    for k in full:
+        assert torch.equal(full[k][3], one[k][0]), k
+
+
+def test_band_equals_whole_bitwise():
+    """Row-band launch (band + halo rows in the buffer) must reproduce the whole-image result exactly."""
+    H, W = 300, 260
+    img = synth(3500, H, W)
+    g = G2Batch()
+    whole = g.run(torch.from_numpy(img[None]).cuda(), capi.G2_MASK_FULL)
+    for (r0, r1) in ((0, 100), (100, 228), (228, 300)):
+        lo, hi = max(0, r0 - 4), min(H, r1 + 4)
+        buf = torch.from_numpy(img[None, lo:hi].copy()).cuda()
+        part = g.run(buf, capi.G2_MASK_FULL, band=Band(full_rows=H, y_origin=lo, row_begin=r0, row_end=r1))
+        for k in whole:
+            assert torch.equal(part[k][0], whole[k][0, r0:r1]), (k, r0, r1)
+
+
+def test_flip_symmetry_and_scaling_4k():
+    """Size-independent properties at full frame size (3840x2160): a horizontal flip mirrors even-x planes and
+    negates odd-x planes; scaling the input by 2 scales the basis exactly by 2 (power-of-two, no rounding)."""
+    rs = np.random.default_rng(123)
+    img = rs.uniform(0, 255, (1, 2160, 3840)).astype(np.float32)
+    g = G2Batch()
+    x = torch.from_numpy(img).cuda()
+    a = g.run(x, capi.G2_MASK_STATE)
+    b = g.run(torch.flip(x, dims=[2]).contiguous(), capi.G2_MASK_STATE)
+    # x-parity of each basis plane = parity of its row (kernelX) tap set: g1 e, g3 o, g2 e, h1 o, h4 e, h3 o, h2 e
+    sign = {"g2a": 1, "g2b": -1, "g2c": 1, "h2a": -1, "h2b": 1, "h2c": -1, "h2d": 1}
+    for k, s in sign.items():
+        assert torch.equal(torch.flip(b[k], dims=[2]), s * a[k]), k
+    c = g.run(x * 2, capi.G2_MASK_STATE)
+    for k in sign:
+        assert torch.equal(c[k], 2 * a[k]), k
+    assert torch.equal(c["theta"], a["theta"])
+    # spot parity on a crop against the oracle (crop far from borders => identical support)
+    o = ref.SteerableFiltersG2(img[0, 1000:1200, 2000:2300])
+    rng = basis_range([getattr(o, k) for k in STATE])
+    for k in STATE:
+        assert_close_range(a[k][0, 1010:1190, 2010:2290].cpu().numpy(), getattr(o, k)[10:-10, 10:-10], rng, "crop " + k)
+
+
+def test_pyramid_levels_vs_oracle():
+    fr = _frames(3600, 2, 135, 241)
+    x = torch.from_numpy(fr).cuda()
+    g = G2Batch()
+    levels = g.run_pyramid(x, 5, capi.G2_MASK_ORIENT)
+    assert [tuple(l["theta"].shape[1:]) for l in levels] == [(135, 241), (68, 121), (34, 61), (17, 31), (9, 16)]
+    for i in range(2):
+        pyr = ref.pyramid(fr[i], 5)
+        cur = x[i:i + 1]
+        for l in range(5):
+            if l:
+                cur = pyr_down(cur)
+                assert float(np.max(np.abs(cur[0].cpu().numpy() - pyr[l]))) <= 1e-4 * 255, f"pyr level {l}"
+            # each level's analysis vs the oracle run on the ORACLE's level (tolerances absorb the 1e-5 level diff)
+            o = ref.SteerableFiltersG2(pyr[l])
+            rng = basis_range([getattr(o, k) for k in STATE])
+            assert_close_range(levels[l]["strength"][i].cpu().numpy(), o.strength, rng * rng, f"L{l} strength")
+            assert_angle_close(levels[l]["theta"][i].cpu().numpy(), o.theta, o.strength, np.pi, f"L{l} theta", thresh_frac=1e-2)
+
+
+@pytest.mark.parametrize("shape", [(1, 7), (3, 3), (2, 9), (37, 51), (64, 64)])
+def test_pyr_down_edge_sizes(shape):
+    img = synth(3700, *shape)
+    out = pyr_down(torch.from_numpy(img[None]).cuda())[0].cpu().numpy()
+    want = ref.pyr_down(img)
+    assert out.shape == want.shape
+    assert float(np.max(np.abs(out - want))) <= 1e-4 * 255

@@ -1,0 +1,85 @@
+"""G4/H4: basis, scalar / map steering, magnitude + phase -- class surface and fused batch path vs the oracle."""
+import numpy as np
+import pytest
+import torch
+
+import cvsteer_b200 as cb
+from cvsteer_b200 import capi
+from cvsteer_b200.batch import G4Batch
+from oracle import cvsteer_ref as ref
+from tests.util import assert_angle_close, assert_close_range, basis_range, synth
+
+pytestmark = pytest.mark.gpu
+P = ref.SteerableFiltersG4.PLANES
+
+
+def test_fish_golden(fish_fixture, fish_oracle):
+    f = cb.SteerableFiltersG4(fish_fixture["fish"].astype(np.float32))
+    rng = basis_range([fish_oracle[k] for k in P])
+    for k in P:
+        assert_close_range(getattr(f, k), fish_oracle[k], rng, k)
+    g4, h4 = f.steer(0.3)
+    assert_close_range(g4, fish_oracle["g4_s03"], rng, "g4(0.3)")
+    assert_close_range(h4, fish_oracle["h4_s03"], rng, "h4(0.3)")
+    assert abs(float(g4[92, 128]) - 191.86337) < 2e-2 and abs(float(h4[92, 128]) - 16.558273) < 2e-2
+    g4, h4, mag, ph = f.steer(fish_oracle["theta"], with_phase=True)
+    assert_close_range(g4, fish_oracle["g4_map"], rng, "g4 map")
+    assert_close_range(h4, fish_oracle["h4_map"], rng, "h4 map")
+    assert_close_range(mag, fish_oracle["mag4"], rng, "mag4")
+    assert_angle_close(ph, fish_oracle["phase4"], fish_oracle["mag4"], 2 * np.pi, "phase4")
+
+
+@pytest.mark.parametrize("shape", [(131, 257), (64, 128), (13, 13), (7, 7), (3, 5), (1, 1), (5, 300)])
+def test_class_vs_oracle(shape):
+    img = synth(4000 + shape[1], *shape)
+    o = ref.SteerableFiltersG4(img)
+    f = cb.SteerableFiltersG4(img)
+    rng = max(basis_range([getattr(o, k) for k in P]), 1.0)
+    for k in P:
+        assert_close_range(getattr(f, k), getattr(o, k), rng, k)
+    for th in (0.3, -1.9):
+        g4, h4 = f.steer(th)
+        w = o.steer_scalar(th)
+        assert_close_range(g4, w[0], rng, "g4 scalar")
+        assert_close_range(h4, w[1], rng, "h4 scalar")
+    th = np.random.default_rng(1).uniform(-3.5, 3.5, shape).astype(np.float32)
+    g4, h4, mag, ph = f.steer(th, with_phase=True)
+    w = o.steer_map_full(th)
+    assert_close_range(g4, w[0], rng, "g4 map")
+    assert_close_range(h4, w[1], rng, "h4 map")
+    assert_close_range(mag, w[2], rng, "mag")
+    assert_angle_close(ph, w[3], w[2], 2 * np.pi, "phase")
+
+
+@pytest.mark.parametrize("width,spacing", [(4, 0.7), (8, 0.4)])
+def test_generic_width(width, spacing):
+    img = synth(4100, 60, 77)
+    o = ref.SteerableFiltersG4(img, width, spacing)
+    f = cb.SteerableFiltersG4(img, width, spacing)
+    rng = basis_range([getattr(o, k) for k in P])
+    for k in P:
+        assert_close_range(getattr(f, k), getattr(o, k), rng, k)
+
+
+def test_fused_batch_steer_phase():
+    """Config 4: steer with a per-pixel theta map -> g4, h4, magnitude, phase in one launch."""
+    fr = np.stack([synth(4200 + i, 150, 260) for i in range(2)])
+    th = np.stack([ref.SteerableFiltersG2(f).theta for f in fr])
+    g = G4Batch()
+    r = g.run(torch.from_numpy(fr).cuda(), capi.G4_MASK_STEER | capi.G4_MASK_BASIS, steer=capi.STEER_MAP,
+              theta_map=torch.from_numpy(th).cuda())
+    for i in range(2):
+        o = ref.SteerableFiltersG4(fr[i])
+        rng = basis_range([getattr(o, k) for k in P])
+        for k in P:
+            assert_close_range(r[k][i].cpu().numpy(), getattr(o, k), rng, k)
+        w = o.steer_map_full(th[i])
+        assert_close_range(r["g4"][i].cpu().numpy(), w[0], rng, "g4")
+        assert_close_range(r["h4"][i].cpu().numpy(), w[1], rng, "h4")
+        assert_close_range(r["magnitude"][i].cpu().numpy(), w[2], rng, "mag")
+        assert_angle_close(r["phase"][i].cpu().numpy(), w[3], w[2], 2 * np.pi, "phase")
+    r2 = g.run(torch.from_numpy(fr).cuda(), capi.G4_MASK_STEER, steer=capi.STEER_SCALAR, theta=0.3)
+    w = ref.SteerableFiltersG4(fr[0]).steer_scalar(0.3)
+    assert_close_range(r2["g4"][0].cpu().numpy(), w[0], 1000.0, "g4 scalar fused")
+    with pytest.raises(capi.CvsError):
+        g.run(torch.from_numpy(fr).cuda(), capi.G4_MASK_STEER)  # no dominant orientation in G4 (reference G4.h:40-41)
