@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcvsteer_b200.so")
+# CVS_LIB selects an alternative build of the same library (used to A/B kernel tuning variants on the GPU box)
+LIB_PATH = os.environ.get("CVS_LIB") or os.path.join(_HERE, "libcvsteer_b200.so")
 
 # ---- enums (mirror include/cvsteer_c.h) ----
 (G2A, G2B, G2C, H2A, H2B, H2C, H2D, C1, C2, C3, THETA, STRENGTH, G2T, H2T, E, MAG, PHASE, EDGES, DARK,

@@ -24,9 +24,26 @@ __host__ __device__ __forceinline__ int reflect101(int p, int n)
     return p;
 }
 
+// Single-instruction SFU approximations (MUFU.RCP / MUFU.SQRT), ~1 ulp; used by the fused kernels where the
+// IEEE sequences (8-10 instructions each) would cost more issue slots than the whole steering step.
+__device__ __forceinline__ float fast_rcp(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_sqrt(float x)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // cv::cartToPolar's angle (hal::fastAtan32f, in radians, range [0, 2pi)): 7th-order odd polynomial in
-// min/max, evaluated with FMAs as OpenCV's SIMD path does.  Verified bit-identical to cv2 4.13.0 on 2M
-// random points when evaluated this way (tests/test_device_math_model.py holds the numpy model).
+// min/max, evaluated with FMAs as OpenCV's SIMD path does.  With FAST = false (IEEE division) this is
+// bit-identical to cv2 4.13.0 on 2M random points; FAST = true replaces the division by MUFU.RCP (<= 2 ulp on
+// the ratio, i.e. ~1e-7 rad).
+template <bool FAST = false>
 __device__ __forceinline__ float cv_atan2(float y, float x)
 {
     constexpr float kDeg = 57.29577951308232f;  // (float)(180/CV_PI)
@@ -36,7 +53,8 @@ __device__ __forceinline__ float cv_atan2(float y, float x)
     constexpr float P7 = -0.04432655554792128f * kDeg;
     const float ax = fabsf(x), ay = fabsf(y);
     const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-    const float c = __fdiv_rn(mn, mx + 2.220446049250313e-16f);  // + (float)DBL_EPSILON: (0,0) -> 0
+    const float den = mx + 2.220446049250313e-16f;  // + (float)DBL_EPSILON: (0,0) -> 0
+    const float c = FAST ? mn * fast_rcp(den) : __fdiv_rn(mn, den);
     const float c2 = c * c;
     float a = fmaf(fmaf(fmaf(P7, c2, P5), c2, P3), c2, P1) * c;
     a = (ay > ax) ? 90.f - a : a;
@@ -47,8 +65,13 @@ __device__ __forceinline__ float cv_atan2(float y, float x)
     return a * 0.017453292519943295f;  // (float)(CV_PI/180)
 }
 
-// cv::cartToPolar's magnitude: sqrt(x*x + y*y) with the inner sum fused, IEEE sqrt.
-__device__ __forceinline__ float cv_magnitude(float x, float y) { return __fsqrt_rn(fmaf(x, x, y * y)); }
+// cv::cartToPolar's magnitude: sqrt(x*x + y*y) with the inner sum fused; IEEE sqrt, or MUFU.SQRT when FAST.
+template <bool FAST = false>
+__device__ __forceinline__ float cv_magnitude(float x, float y)
+{
+    const float q = fmaf(x, x, y * y);
+    return FAST ? fast_sqrt(q) : __fsqrt_rn(q);
+}
 
 // SteerableFilters::wrap: a > float(pi) -> float(double(a) - 2pi).  float(2pi) = 2pi + 1.7484555e-7, the
 // first subtraction is exact (Sterbenz), the correction restores the double-precision result.
@@ -62,6 +85,7 @@ struct Orientation {
 };
 
 // G2.cpp:70-99 on the 7 basis values of one pixel.
+template <bool FAST = false>
 __device__ __forceinline__ Orientation orientation_g2(float a, float b, float c, float ha, float hb, float hc,
                                                      float hd)
 {
@@ -85,8 +109,8 @@ __device__ __forceinline__ Orientation orientation_g2(float a, float b, float c,
     o.c1 = c1;
     o.c2 = c2;
     o.c3 = c3;
-    o.strength = cv_magnitude(c2, c3);
-    o.theta = 0.5f * wrap_pi(cv_atan2(c3, c2));
+    o.strength = cv_magnitude<FAST>(c2, c3);
+    o.theta = 0.5f * wrap_pi(cv_atan2<FAST>(c3, c2));
     return o;
 }
 
@@ -112,20 +136,22 @@ __device__ __forceinline__ void steer_g4(float ct, float st, const float* g /*5*
 }
 
 // G2.cpp:107-112
+template <bool FAST = false>
 __device__ __forceinline__ void magnitude_phase(float g, float h, float& mag, float& phase)
 {
-    mag = cv_magnitude(g, h);
-    float p = wrap_pi(cv_atan2(h, g));
+    mag = cv_magnitude<FAST>(g, h);
+    float p = wrap_pi(cv_atan2<FAST>(h, g));
     phase = (p != p) ? 0.f : p;  // cv::patchNaNs
 }
 
 // G2.cpp:179-186: lambda = cos^2(err) gated at pi/2.
+template <bool FAST = false>
 __device__ __forceinline__ float phase_weight(float phase, float phi, bool signum)
 {
     float err = signum ? fabsf(phase - phi) : fabsf(fabsf(phase) - fabsf(phi));
     const float alt = (6.28318548202514648f - err) - 1.7484555e-7f;  // float(2*M_PI - err)
     err = fminf(err, alt);
-    const float ct = cosf(err);
+    const float ct = FAST ? __cosf(err) : cosf(err);  // err in [0, pi]
     return (fabsf(err) > 1.57079637050628662f) ? 0.f : ct * ct;
 }
 

@@ -7,47 +7,68 @@
 #pragma once
 #include "../../include/cvsteer_c.h"
 #include "march.cuh"
+#include "taps_baked.inc"
 
 namespace cvs {
 
+#ifndef CVS_G2_BH
+#define CVS_G2_BH 64
+#endif
+#ifndef CVS_G2_MIN_CTAS
+#define CVS_G2_MIN_CTAS 4
+#endif
 struct G2Fam {
-    static constexpr int R = 4, NSETS = 6, NROW = 6, NBASIS = 7, BH = 64, MIN_CTAS = 4;
+    static constexpr int R = 4, NSETS = 6, NROW = 5, NBASIS = 7, BH = CVS_G2_BH, MIN_CTAS = CVS_G2_MIN_CTAS;
     // unique tap sets: 0 g1, 1 g2(=h2), 2 g3, 3 h1, 4 h3, 5 h4   (index into TapTable::t)
     // map from the API's 7 tap sets (g1,g2,g3,h1,h2,h3,h4) to unique sets
     __host__ __device__ static constexpr int unique_of(int api) { constexpr int t[7] = {0, 1, 2, 3, 1, 4, 5}; return t[api]; }
     __host__ __device__ static constexpr bool set_odd(int s) { return s == 2 || s == 3 || s == 4; }
-    // row-filtered planes: one per unique set
-    __host__ __device__ static constexpr int row_set(int p) { return p; }
-    __host__ __device__ static constexpr bool row_odd(int p) { return set_odd(p); }
-    // basis planes (CVS_G2A..CVS_H2D):  row(kernelX) set, column(kernelY) set
-    //   G2a (g1,g2)  G2b (g3,g3)  G2c (g2,g1)  H2a (h1,h2)  H2b (h4,h3)  H2c (h3,h4)  H2d (h2,h1)
-    __host__ __device__ static constexpr int basis_row(int q) { constexpr int t[7] = {0, 2, 1, 3, 5, 4, 1}; return t[q]; }
+    // Row-filtered planes kept in the register window: g1, g2(=h2), h1, h3, h4.  There is no g3 plane: g3(x) =
+    // sqrt(1.843) x exp(-x^2) is h3(x) = x exp(-x^2) times a constant, so G2b = (g3 row)(g3 col) is computed from the h3
+    // row plane with the column taps pre-scaled by that constant (TapTable set 2, see fill_tap_table).  One row
+    // pass and nine window registers less; the result moves by <= 1 ulp of the taps (1e-7 of range).
+    __host__ __device__ static constexpr int row_set(int p) { constexpr int t[5] = {0, 1, 3, 4, 5}; return t[p]; }
+    __host__ __device__ static constexpr bool row_odd(int p) { return set_odd(row_set(p)); }
+    // basis planes (CVS_G2A..CVS_H2D):  row(kernelX) plane, column(kernelY) set
+    //   G2a (g1,g2)  G2b (g3~h3,g3')  G2c (g2,g1)  H2a (h1,h2)  H2b (h4,h3)  H2c (h3,h4)  H2d (h2,h1)
+    __host__ __device__ static constexpr int basis_row(int q) { constexpr int t[7] = {0, 3, 1, 2, 4, 3, 1}; return t[q]; }
     __host__ __device__ static constexpr int basis_set(int q) { constexpr int t[7] = {1, 2, 0, 1, 4, 5, 3}; return t[q]; }
     __host__ __device__ static constexpr bool basis_odd(int q) { return set_odd(basis_set(q)); }
+    // TapTable row kScaledSet = taps of API set kScaledFromApi times the ratio (API set kScaleNumApi / API set kScaleDenApi):
+    // here g3 * (g3/h3), overwriting g3's own row (plain g3 is no longer used anywhere).
+    static constexpr int kScaledSet = 2, kScaledFromApi = 2, kScaleNumApi = 2, kScaleDenApi = 5;
+    // reference-default taps (width 4, spacing 0.67f) as compile-time constants -> FFMA immediates
+    static constexpr int kBakedWidth = CVS_BAKED_G2_WIDTH;
+    __host__ __device__ static constexpr float baked(int set, int i) { constexpr float t[NSETS][R + 1] = CVS_BAKED_G2_TAPS; return t[set][i]; }
 
     static constexpr unsigned kNeedsOrient = 0x000FFF80u;   // anything beyond the 7 basis planes
     static constexpr unsigned kNeedsSteer = CVS_BIT(CVS_G2T) | CVS_BIT(CVS_H2T) | CVS_BIT(CVS_MAG) | CVS_BIT(CVS_PHASE) |
                                             CVS_BIT(CVS_EDGES) | CVS_BIT(CVS_DARK) | CVS_BIT(CVS_BRIGHT);
 
     // Fused epilogue on the 7 basis values of one pixel.  MASK != 0: compile-time plane set, steering at the
-    // in-kernel dominant angle.  MASK == 0: run-time mask and steer source.
+    // in-kernel dominant angle, SFU approximations for 1/x, sqrt and sin/cos (all far inside the 1e-4-of-range /
+    // 1e-3 rad parity budget).  MASK == 0: run-time mask and steer source, accurate sincosf for arbitrary angles.
+    // `row_off` is warp-uniform (frame + row byte offset); stores are predicated on `xin`, nothing else diverges.
     template <unsigned MASK>
-    __device__ __forceinline__ static void epilogue(const float (&b)[NBASIS], const MarchArgs& a, long long row_off, int x)
+    __device__ __forceinline__ static void epilogue(const float (&b)[NBASIS], const MarchArgs& a, long long row_off, int x, bool xin)
     {
+        constexpr bool FAST = MASK != 0;
         const unsigned m = MASK ? MASK : a.mask;
-        const long long off = row_off + 4ll * x;
-        auto put = [&](int p, float v) { *reinterpret_cast<float*>(reinterpret_cast<char*>(a.out[p]) + off) = v; };
+        const long long off = row_off + 4ll * x;  // one per-thread byte offset shared by every plane
+        auto put = [&](int p, float v) {
+            if (xin) *reinterpret_cast<float*>(reinterpret_cast<char*>(a.out[p]) + off) = v;
+        };
 #pragma unroll
         for (int q = 0; q < NBASIS; ++q)
             if (m & (1u << q)) put(q, b[q]);
         if (!(m & kNeedsOrient)) return;
 
         const int src = MASK ? (int)CVS_STEER_DOMINANT : a.steer_source;
-        dev::Orientation o;
+        dev::Orientation o{};
         const bool need_orient = (m & (CVS_BIT(CVS_C1) | CVS_BIT(CVS_C2) | CVS_BIT(CVS_C3) | CVS_BIT(CVS_THETA) |
                                        CVS_BIT(CVS_STRENGTH) | CVS_BIT(CVS_E))) || src == CVS_STEER_DOMINANT;
         if (need_orient) {
-            o = dev::orientation_g2(b[0], b[1], b[2], b[3], b[4], b[5], b[6]);
+            o = dev::orientation_g2<FAST>(b[0], b[1], b[2], b[3], b[4], b[5], b[6]);
             if (m & CVS_BIT(CVS_C1)) put(CVS_C1, o.c1);
             if (m & CVS_BIT(CVS_C2)) put(CVS_C2, o.c2);
             if (m & CVS_BIT(CVS_C3)) put(CVS_C3, o.c3);
@@ -56,76 +77,90 @@ struct G2Fam {
         }
         if (!(m & (kNeedsSteer | CVS_BIT(CVS_E)))) return;
 
-        if (src == CVS_STEER_DOMINANT && !(m & kNeedsSteer)) {
-            // E(theta_d) = c1 + c2 cos(2 theta_d) + c3 sin(2 theta_d) = c1 + strength (G2.cpp:174-176 at theta_d)
-            put(CVS_E, o.c1 + o.strength);
-            return;
-        }
         float ct, st;
-        if (src == CVS_STEER_SCALAR) {
-            ct = a.cos_t;
-            st = a.sin_t;
+        if (src == CVS_STEER_DOMINANT) {
+            // E(theta_d) = c1 + c2 cos(2 theta_d) + c3 sin(2 theta_d) = c1 + strength  (G2.cpp:174-176 at theta_d)
+            if (m & CVS_BIT(CVS_E)) put(CVS_E, o.c1 + o.strength);
+            if (!(m & kNeedsSteer)) return;
+            if (FAST) __sincosf(o.theta, &st, &ct);  // |theta_d| <= pi/2: MUFU.SIN/COS abs error < 5e-7
+            else sincosf(o.theta, &st, &ct);
         } else {
-            const float th = (src == CVS_STEER_DOMINANT)
-                                 ? o.theta
-                                 : *reinterpret_cast<const float*>(reinterpret_cast<const char*>(a.theta_map) + off);
-            sincosf(th, &st, &ct);
-        }
-        if (m & CVS_BIT(CVS_E)) {
+            if (src == CVS_STEER_SCALAR) {
+                ct = a.cos_t;
+                st = a.sin_t;
+            } else {
+                sincosf(*reinterpret_cast<const float*>(reinterpret_cast<const char*>(a.theta_map) + (xin ? off : row_off)), &st, &ct);
+            }
             // cos 2t = c^2 - s^2, sin 2t = 2cs  (reference: polarToCart(2*theta), G2.cpp:175)
-            put(CVS_E, fmaf(o.c2, fmaf(ct, ct, -st * st), fmaf(o.c3, 2.f * ct * st, o.c1)));
+            if (m & CVS_BIT(CVS_E)) put(CVS_E, fmaf(o.c2, fmaf(ct, ct, -st * st), fmaf(o.c3, 2.f * ct * st, o.c1)));
+            if (!(m & kNeedsSteer)) return;
         }
-        if (!(m & kNeedsSteer)) return;
         float g2, h2;
         dev::steer_g2(ct, st, b[0], b[1], b[2], b[3], b[4], b[5], b[6], g2, h2);
         if (m & CVS_BIT(CVS_G2T)) put(CVS_G2T, g2);
         if (m & CVS_BIT(CVS_H2T)) put(CVS_H2T, h2);
         if (m & (kNeedsSteer & ~(CVS_BIT(CVS_G2T) | CVS_BIT(CVS_H2T)))) {
             float mag, ph;
-            dev::magnitude_phase(g2, h2, mag, ph);
+            dev::magnitude_phase<FAST>(g2, h2, mag, ph);
             if (m & CVS_BIT(CVS_MAG)) put(CVS_MAG, mag);
             if (m & CVS_BIT(CVS_PHASE)) put(CVS_PHASE, ph);
             // find*(magnitude, phase): both reference callers feed magnitude (example/steer.cpp:88-90)
-            if (m & CVS_BIT(CVS_EDGES)) put(CVS_EDGES, mag * dev::phase_weight(ph, 1.57079637050628662f, false));
-            if (m & CVS_BIT(CVS_DARK)) put(CVS_DARK, mag * dev::phase_weight(ph, 0.f, true));
-            if (m & CVS_BIT(CVS_BRIGHT)) put(CVS_BRIGHT, mag * dev::phase_weight(ph, 3.14159274101257324f, true));
+            if (m & CVS_BIT(CVS_EDGES)) put(CVS_EDGES, mag * dev::phase_weight<FAST>(ph, 1.57079637050628662f, false));
+            if (m & CVS_BIT(CVS_DARK)) put(CVS_DARK, mag * dev::phase_weight<FAST>(ph, 0.f, true));
+            if (m & CVS_BIT(CVS_BRIGHT)) put(CVS_BRIGHT, mag * dev::phase_weight<FAST>(ph, 3.14159274101257324f, true));
         }
     }
 };
 
+#ifndef CVS_G4_BH
+#define CVS_G4_BH 64
+#endif
+#ifndef CVS_G4_MIN_CTAS
+#define CVS_G4_MIN_CTAS 2
+#endif
 struct G4Fam {
-    static constexpr int R = 6, NSETS = 10, NROW = 10, NBASIS = 11, BH = 64, MIN_CTAS = 2;
-    // unique tap sets: 0 g1, 1 g2(=h2), 2 g3, 3 g4, 4 g5, 5 h1, 6 h3, 7 h4, 8 h5, 9 h6
+    static constexpr int R = 6, NSETS = 11, NROW = 9, NBASIS = 11, BH = CVS_G4_BH, MIN_CTAS = CVS_G4_MIN_CTAS;
+    // tap table rows: 0 g1, 1 g2(=h2), 2 g3, 3 g4, 4 g5, 5 h1, 6 h3, 7 h4, 8 h5, 9 h6, 10 g3 * (g4/h4)
     // API order g1..g5,h1..h6
     __host__ __device__ static constexpr int unique_of(int api) { constexpr int t[11] = {0, 1, 2, 3, 4, 5, 1, 6, 7, 8, 9}; return t[api]; }
-    __host__ __device__ static constexpr bool set_odd(int s) { return s == 2 || s == 3 || s == 5 || s == 7 || s == 8; }
-    __host__ __device__ static constexpr int row_set(int p) { return p; }
-    __host__ __device__ static constexpr bool row_odd(int p) { return set_odd(p); }
-    //   G4a (g1,g2) G4b (g3,g4) G4c (g5,g5) G4d (g4,g3) G4e (g2,g1)
+    __host__ __device__ static constexpr bool set_odd(int s) { return s == 2 || s == 3 || s == 5 || s == 7 || s == 8 || s == 10; }
+    // Row planes in the window: g1, g2(=h2), g3, g5, h1, h3, h4, h5, h6.  No g4 plane: g4(x) = 1.246 x exp(-x^2) is h4(x)
+    // times a constant, so G4d = (g4 row)(g3 col) comes from the h4 row plane with g3's column taps pre-scaled by that
+    // constant (table row 10).  Plain g3 (row pass of G4b) and plain g4 (column pass of G4b) stay in rows 2 and 3.
+    __host__ __device__ static constexpr int row_set(int p) { constexpr int t[9] = {0, 1, 2, 4, 5, 6, 7, 8, 9}; return t[p]; }
+    __host__ __device__ static constexpr bool row_odd(int p) { return set_odd(row_set(p)); }
+    //   G4a (g1,g2) G4b (g3,g4) G4c (g5,g5) G4d (g4~h4,g3') G4e (g2,g1)
     //   H4a (h1,h2) H4b (h3,h4) H4c (h5,h6) H4d (h6,h5) H4e (h4,h3) H4f (h2,h1)
-    __host__ __device__ static constexpr int basis_row(int q) { constexpr int t[11] = {0, 2, 4, 3, 1, 5, 6, 8, 9, 7, 1}; return t[q]; }
-    __host__ __device__ static constexpr int basis_set(int q) { constexpr int t[11] = {1, 3, 4, 2, 0, 1, 7, 9, 8, 6, 5}; return t[q]; }
+    // row planes:      g1=0 g2=1 g3=2 g5=3 h1=4 h3=5 h4=6 h5=7 h6=8
+    __host__ __device__ static constexpr int basis_row(int q) { constexpr int t[11] = {0, 2, 3, 6, 1, 4, 5, 7, 8, 6, 1}; return t[q]; }
+    __host__ __device__ static constexpr int basis_set(int q) { constexpr int t[11] = {1, 3, 4, 10, 0, 1, 7, 9, 8, 6, 5}; return t[q]; }
     __host__ __device__ static constexpr bool basis_odd(int q) { return set_odd(basis_set(q)); }
+    static constexpr int kScaledSet = 10, kScaledFromApi = 2, kScaleNumApi = 3, kScaleDenApi = 8;  // g3 * (g4/h4)
+    static constexpr int kBakedWidth = CVS_BAKED_G4_WIDTH;
+    __host__ __device__ static constexpr float baked(int set, int i) { constexpr float t[NSETS][R + 1] = CVS_BAKED_G4_TAPS; return t[set][i]; }
 
     static constexpr unsigned kNeedsSteer = CVS_G4_MASK_STEER;
 
+    // MASK != 0: compile-time plane set, steering at a per-pixel angle map (config 4), SFU approximations.
     template <unsigned MASK>
-    __device__ __forceinline__ static void epilogue(const float (&b)[NBASIS], const MarchArgs& a, long long row_off, int x)
+    __device__ __forceinline__ static void epilogue(const float (&b)[NBASIS], const MarchArgs& a, long long row_off, int x, bool xin)
     {
+        constexpr bool FAST = MASK != 0;
         const unsigned m = MASK ? MASK : a.mask;
-        const long long off = row_off + 4ll * x;
-        auto put = [&](int p, float v) { *reinterpret_cast<float*>(reinterpret_cast<char*>(a.out[p]) + off) = v; };
+        const long long off = row_off + 4ll * x;  // one per-thread byte offset shared by every plane
+        auto put = [&](int p, float v) {
+            if (xin) *reinterpret_cast<float*>(reinterpret_cast<char*>(a.out[p]) + off) = v;
+        };
 #pragma unroll
         for (int q = 0; q < NBASIS; ++q)
             if (m & (1u << q)) put(q, b[q]);
         if (!(m & kNeedsSteer)) return;
         float ct, st;
-        if (a.steer_source == CVS_STEER_SCALAR) {
+        if (!MASK && a.steer_source == CVS_STEER_SCALAR) {
             ct = a.cos_t;
             st = a.sin_t;
         } else {
-            const float th = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(a.theta_map) + off);
-            sincosf(th, &st, &ct);
+            sincosf(*reinterpret_cast<const float*>(reinterpret_cast<const char*>(a.theta_map) + (xin ? off : row_off)), &st, &ct);
         }
         float g4, h4;
         dev::steer_g4(ct, st, &b[0], &b[5], g4, h4);
@@ -133,7 +168,7 @@ struct G4Fam {
         if (m & CVS_BIT(CVS_H4T)) put(CVS_H4T, h4);
         if (m & (CVS_BIT(CVS_MAG4) | CVS_BIT(CVS_PHASE4))) {
             float mag, ph;
-            dev::magnitude_phase(g4, h4, mag, ph);
+            dev::magnitude_phase<FAST>(g4, h4, mag, ph);
             if (m & CVS_BIT(CVS_MAG4)) put(CVS_MAG4, mag);
             if (m & CVS_BIT(CVS_PHASE4)) put(CVS_PHASE4, ph);
         }

@@ -68,7 +68,7 @@ __global__ void k_generic_cols(const __grid_constant__ MarchArgs a, const __grid
         for (int q = 0; q < Fam::NBASIS; ++q) b[q] = fmaf(taps.t[Fam::basis_set(q)][i + w], v[Fam::basis_row(q)], b[q]);
     }
     const long long row_off = (long long)frame * a.out_frame_stride + (long long)(y - a.out_row_origin) * a.out_pitch;
-    Fam::template epilogue<0>(b, a, row_off, x);
+    Fam::template epilogue<0>(b, a, row_off, x, true);
 }
 
 template <class Fam>
@@ -80,6 +80,7 @@ static cudaError_t launch_generic(const FamilyTaps& ft, const BatchGeom& g, cons
     memset(&wt, 0, sizeof(wt));
     wt.width = ft.width;
     for (int api = 0; api < ft.nsets; ++api) memcpy(wt.t[Fam::unique_of(api)], ft.t[api], sizeof(float) * (2 * ft.width + 1));
+    scale_taps_by_ratio(ft.t[Fam::kScaledFromApi], ft.t[Fam::kScaleNumApi], ft.t[Fam::kScaleDenApi], 2 * ft.width + 1, wt.t[Fam::kScaledSet]);
     const dim3 block(128);
     const dim3 grid_r((g.cols + 127) / 128, g.buf_rows), grid_c((g.cols + 127) / 128, g.out_row_end - g.out_row_begin);
     for (int f = 0; f < g.n; ++f) {

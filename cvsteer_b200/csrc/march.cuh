@@ -165,13 +165,14 @@ __device__ __forceinline__ void load_tile_manual(float* tile, const MarchArgs& a
 //   basis_row[NBASIS], basis_set[NBASIS], basis_odd[NBASIS]   row plane / column tap set / parity per basis plane
 //   static void epilogue<MASK>(const float (&b)[NBASIS], const MarchArgs&, long long out_off, long long th_off)
 // ------------------------------------------------------------------------------------------------
-template <class Fam, unsigned MASK /* 0 = use a.mask at run time */, bool USE_TMA, typename TIn>
+template <class Fam, unsigned MASK /* 0 = use a.mask at run time */, bool USE_TMA, typename TIn, bool BAKED>
 __global__ void __launch_bounds__(MARCH_TW, Fam::MIN_CTAS)
 k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchArgs a,
         const __grid_constant__ TapTable<Fam::NSETS, Fam::R> taps)
 {
     constexpr int R = Fam::R, K = 2 * R + 1, TW = MARCH_TW, TWH = march_tile_width(R), BH = Fam::BH, TROWS = BH + 2 * R;
     constexpr int NROW = Fam::NROW, NB = Fam::NBASIS;
+    static_assert(K <= 13, "extend the slot switch");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* tile = reinterpret_cast<float*>(smem_raw);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + sizeof(float) * TROWS * TWH);
@@ -204,10 +205,19 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
     int nrows = a.out_row_end - yb;
     nrows = nrows < BH ? nrows : BH;
 
-    float win[NROW][K];
+    // Taps: FFMA immediates when the handle's taps are the baked reference defaults, else constant-bank operands
+    // straight out of the kernel parameter block.
+    auto tap = [&](int set, int i) -> float {
+        if constexpr (BAKED) return Fam::baked(set, i);
+        else return taps.t[set][i];
+    };
 
-    // all unique row passes of one tile row -> slot `slot` of every window
-    auto row_pass = [&](int rt, auto slot_c) {
+    float win[NROW][K];  // (2R+1)-row register window per row-filtered plane; slot indices are compile-time
+    float b[NB];
+
+    // One tile row: all unique row passes into window slot `slot`; then, once the window is full, all column passes.
+    // Even/odd symmetry: R sums + R differences are shared by every filter of the pass.
+    auto row_col = [&](int rt, auto slot_c) {
         constexpr int slot = decltype(slot_c)::value;
         const float* src = tcol + rt * TWH;
         float v[K];
@@ -226,65 +236,60 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
             const int set = Fam::row_set(p);
             float acc;
             if (Fam::row_odd(p)) {
-                acc = taps.t[set][1] * d[1];
+                acc = tap(set, 1) * d[1];
 #pragma unroll
-                for (int i = 2; i <= R; ++i) acc = fmaf(taps.t[set][i], d[i], acc);
+                for (int i = 2; i <= R; ++i) acc = fmaf(tap(set, i), d[i], acc);
             } else {
-                acc = taps.t[set][0] * s[0];
+                acc = tap(set, 0) * s[0];
 #pragma unroll
-                for (int i = 1; i <= R; ++i) acc = fmaf(taps.t[set][i], s[i], acc);
+                for (int i = 1; i <= R; ++i) acc = fmaf(tap(set, i), s[i], acc);
             }
             win[p][slot] = acc;
         }
-    };
-
-    // all column passes for the window whose newest row sits in `slot`, then the epilogue
-    auto col_pass_and_emit = [&](int y, auto slot_c) {
-        constexpr int slot = decltype(slot_c)::value;
-        constexpr int ctr = (slot + K - R) % K;  // slot of the centre row
-        float b[NB];
+        if (rt >= 2 * R) {  // CTA-uniform: the first 2R rows only feed the window
+            constexpr int ctr = (slot + K - R) % K;  // slot of the centre row
 #pragma unroll
-        for (int q = 0; q < NB; ++q) {
-            const int rp = Fam::basis_row(q), set = Fam::basis_set(q);
-            float acc;
-            if (Fam::basis_odd(q)) {
-                acc = taps.t[set][1] * (win[rp][(ctr + 1) % K] - win[rp][(ctr + K - 1) % K]);
+            for (int q = 0; q < NB; ++q) {
+                const int rp = Fam::basis_row(q), set = Fam::basis_set(q);
+                float acc;
+                if (Fam::basis_odd(q)) {
+                    acc = tap(set, 1) * (win[rp][(ctr + 1) % K] - win[rp][(ctr + K - 1) % K]);
 #pragma unroll
-                for (int i = 2; i <= R; ++i)
-                    acc = fmaf(taps.t[set][i], win[rp][(ctr + i) % K] - win[rp][(ctr + K - i) % K], acc);
-            } else {
-                acc = taps.t[set][0] * win[rp][ctr];
+                    for (int i = 2; i <= R; ++i)
+                        acc = fmaf(tap(set, i), win[rp][(ctr + i) % K] - win[rp][(ctr + K - i) % K], acc);
+                } else {
+                    acc = tap(set, 0) * win[rp][ctr];
 #pragma unroll
-                for (int i = 1; i <= R; ++i)
-                    acc = fmaf(taps.t[set][i], win[rp][(ctr + i) % K] + win[rp][(ctr + K - i) % K], acc);
+                    for (int i = 1; i <= R; ++i)
+                        acc = fmaf(tap(set, i), win[rp][(ctr + i) % K] + win[rp][(ctr + K - i) % K], acc);
+                }
+                b[q] = acc;
             }
-            b[q] = acc;
-        }
-        if (xin) {
-            const long long row_off = (long long)frame * a.out_frame_stride + (long long)(y - a.out_row_origin) * a.out_pitch;
-            Fam::template epilogue<MASK>(b, a, row_off, x);
         }
     };
 
-    // pre-roll: the first 2R tile rows only feed the window
-    {
-        auto pre = [&](auto rt_c) { row_pass(decltype(rt_c)::value, rt_c); };
-        [&]<int... I>(std::integer_sequence<int, I...>) { (pre(std::integral_constant<int, I>{}), ...); }
-        (std::make_integer_sequence<int, 2 * R>{});
-    }
-    // main loop, unrolled by K so that every window index is a compile-time constant (register rotation)
+    // The window rotates by one slot per row.  Register files cannot be indexed dynamically, so the row/column code
+    // exists once per slot (a K-way switch); everything that does not depend on the slot -- the whole point-wise
+    // epilogue -- follows the switch ONCE, which keeps the loop body inside the instruction cache.
+    long long row_off = (long long)frame * a.out_frame_stride + (long long)(yb - a.out_row_origin) * a.out_pitch;
+    int slot = 0;
 #pragma unroll 1
-    for (int j = 0; j < nrows; j += K) {
-        auto step = [&](auto ph_c) {
-            constexpr int ph = decltype(ph_c)::value;
-            constexpr int slot = (2 * R + ph) % K;
-            if (j + ph < nrows) {
-                row_pass(2 * R + j + ph, std::integral_constant<int, slot>{});
-                col_pass_and_emit(yb + j + ph, std::integral_constant<int, slot>{});
-            }
-        };
-        [&]<int... I>(std::integer_sequence<int, I...>) { (step(std::integral_constant<int, I>{}), ...); }
-        (std::make_integer_sequence<int, K>{});
+    for (int rt = 0; rt < nrows + 2 * R; ++rt) {
+        switch (slot) {
+#define CVS_CASE(I)                                          \
+    case I:                                                  \
+        if constexpr (I < K) row_col(rt, std::integral_constant<int, (I < K ? I : 0)>{}); \
+        break;
+            CVS_CASE(0) CVS_CASE(1) CVS_CASE(2) CVS_CASE(3) CVS_CASE(4) CVS_CASE(5) CVS_CASE(6) CVS_CASE(7) CVS_CASE(8)
+            CVS_CASE(9) CVS_CASE(10) CVS_CASE(11) CVS_CASE(12)
+#undef CVS_CASE
+            default: break;
+        }
+        slot = (slot + 1 == K) ? 0 : slot + 1;
+        if (rt >= 2 * R) {
+            Fam::template epilogue<MASK>(b, a, row_off, x, xin);
+            row_off += a.out_pitch;
+        }
     }
 }
 

@@ -10,9 +10,9 @@ cudaError_t launch_march_g2(const FamilyTaps& taps, const BatchGeom& g, const Ma
     const int out_rows = g.out_row_end - g.out_row_begin;
     const dim3 grid((g.cols + MARCH_TW - 1) / MARCH_TW, (out_rows + G2Fam::BH - 1) / G2Fam::BH, g.n);
     const unsigned mask = a.mask;
-    if (dom && mask == CVS_G2_MASK_ORIENT) return launch_march_mask<G2Fam, CVS_G2_MASK_ORIENT>(g, a, tt, grid, stream, info, "g2_march<M1>");
-    if (dom && mask == CVS_G2_MASK_FULL) return launch_march_mask<G2Fam, CVS_G2_MASK_FULL>(g, a, tt, grid, stream, info, "g2_march<M2>");
-    if (dom && mask == CVS_G2_MASK_STATE) return launch_march_mask<G2Fam, CVS_G2_MASK_STATE>(g, a, tt, grid, stream, info, "g2_march<M0>");
+    if (dom && mask == CVS_G2_MASK_ORIENT) return launch_march_mask<G2Fam, CVS_G2_MASK_ORIENT, true>(g, a, tt, grid, stream, info, "g2_march<M1>");
+    if (dom && mask == CVS_G2_MASK_FULL) return launch_march_mask<G2Fam, CVS_G2_MASK_FULL, true>(g, a, tt, grid, stream, info, "g2_march<M2>");
+    if (dom && mask == CVS_G2_MASK_STATE) return launch_march_mask<G2Fam, CVS_G2_MASK_STATE, true>(g, a, tt, grid, stream, info, "g2_march<M0>");
     return launch_march_mask<G2Fam, 0u>(g, a, tt, grid, stream, info, "g2_march<dyn>");
 }
 

@@ -11,6 +11,9 @@ cudaError_t launch_march_g4(const FamilyTaps& taps, const BatchGeom& g, const Ma
     fill_tap_table<G4Fam>(taps, tt);
     const int out_rows = g.out_row_end - g.out_row_begin;
     const dim3 grid((g.cols + MARCH_TW - 1) / MARCH_TW, (out_rows + G4Fam::BH - 1) / G4Fam::BH, g.n);
+    const bool map = a.steer_source == CVS_STEER_MAP;
+    if (map && a.mask == CVS_G4_MASK_STEER) return launch_march_mask<G4Fam, CVS_G4_MASK_STEER, true>(g, a, tt, grid, stream, info, "g4_march<steer>");
+    if (a.mask == CVS_G4_MASK_BASIS) return launch_march_mask<G4Fam, CVS_G4_MASK_BASIS, true>(g, a, tt, grid, stream, info, "g4_march<basis>");
     return launch_march_mask<G4Fam, 0u>(g, a, tt, grid, stream, info, "g4_march<dyn>");
 }
 

@@ -74,15 +74,18 @@ static void fill_tap_table(const FamilyTaps& ft, TapTable<Fam::NSETS, Fam::R>& t
         const int u = Fam::unique_of(api);
         for (int i = 0; i <= Fam::R; ++i) tt.t[u][i] = ft.t[api][Fam::R + i];
     }
+    float scaled[MAX_TAPS];
+    scale_taps_by_ratio(ft.t[Fam::kScaledFromApi], ft.t[Fam::kScaleNumApi], ft.t[Fam::kScaleDenApi], 2 * Fam::R + 1, scaled);
+    for (int i = 0; i <= Fam::R; ++i) tt.t[Fam::kScaledSet][i] = scaled[Fam::R + i];
 }
 
-template <class Fam, unsigned MASK, bool TMA, typename TIn>
+template <class Fam, unsigned MASK, bool TMA, typename TIn, bool BAKED>
 static cudaError_t launch_march_one(const CUtensorMap& tm, const MarchArgs& a, const TapTable<Fam::NSETS, Fam::R>& tt, dim3 grid,
                                     cudaStream_t stream, LaunchInfo* info, const char* name)
 {
     constexpr int TROWS = Fam::BH + 2 * Fam::R, TWH = march_tile_width(Fam::R);
     constexpr int smem = TROWS * TWH * (int)sizeof(float) + 16;
-    auto kfn = k_march<Fam, MASK, TMA, TIn>;
+    auto kfn = k_march<Fam, MASK, TMA, TIn, BAKED>;
     static std::once_flag once;  // one per instantiation
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [&] {
@@ -102,7 +105,23 @@ static cudaError_t launch_march_one(const CUtensorMap& tm, const MarchArgs& a, c
     return cudaGetLastError();
 }
 
-template <class Fam, unsigned MASK>
+// true when the handle's taps are bit-identical to the baked reference defaults of the family
+template <class Fam>
+static bool taps_are_baked(const TapTable<Fam::NSETS, Fam::R>& tt)
+{
+    static const bool disabled = getenv("CVS_NO_BAKED") != nullptr;  // A/B switch: constant-bank taps everywhere
+    if (disabled) return false;
+    for (int s = 0; s < Fam::NSETS; ++s)
+        for (int i = 0; i <= Fam::R; ++i) {
+            const float bk = Fam::baked(s, i);
+            if (memcmp(&bk, &tt.t[s][i], sizeof(float)) != 0) return false;
+        }
+    return true;
+}
+
+// BAKED_OK: whether a baked-tap instantiation exists for this mask (kept to the hot static-mask variants to bound
+// compile time and binary size).
+template <class Fam, unsigned MASK, bool BAKED_OK = false>
 static cudaError_t launch_march_mask(const BatchGeom& g, const MarchArgs& a, const TapTable<Fam::NSETS, Fam::R>& tt, dim3 grid,
                                      cudaStream_t stream, LaunchInfo* info, const char* name)
 {
@@ -111,15 +130,21 @@ static cudaError_t launch_march_mask(const BatchGeom& g, const MarchArgs& a, con
     constexpr int TROWS = Fam::BH + 2 * Fam::R, TWH = march_tile_width(Fam::R);
     char nm[96];
     if (tma_eligible(g, Fam::R) && make_tmap(&tm, g, TWH, TROWS)) {
+        if constexpr (BAKED_OK) {
+            if (taps_are_baked<Fam>(tt)) {
+                snprintf(nm, sizeof(nm), "%s/tma/imm-taps", name);
+                return launch_march_one<Fam, MASK, true, float, true>(tm, a, tt, grid, stream, info, nm);
+            }
+        }
         snprintf(nm, sizeof(nm), "%s/tma", name);
-        return launch_march_one<Fam, MASK, true, float>(tm, a, tt, grid, stream, info, nm);
+        return launch_march_one<Fam, MASK, true, float, false>(tm, a, tt, grid, stream, info, nm);
     }
     if (g.in_u8) {
         snprintf(nm, sizeof(nm), "%s/ldg-u8", name);
-        return launch_march_one<Fam, MASK, false, unsigned char>(tm, a, tt, grid, stream, info, nm);
+        return launch_march_one<Fam, MASK, false, unsigned char, false>(tm, a, tt, grid, stream, info, nm);
     }
     snprintf(nm, sizeof(nm), "%s/ldg", name);
-    return launch_march_one<Fam, MASK, false, float>(tm, a, tt, grid, stream, info, nm);
+    return launch_march_one<Fam, MASK, false, float, false>(tm, a, tt, grid, stream, info, nm);
 }
 
 static inline MarchArgs make_args(const BatchGeom& g, unsigned mask, const SteerSpec& st, float* const* outs, int nplanes)

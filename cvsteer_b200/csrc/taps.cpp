@@ -50,6 +50,15 @@ void sample(TapFn f, int width, float spacing, float* dst)
 const int kG2TapOdd[G2_NUM_TAPSETS] = {0, 0, 1, 1, 0, 1, 0};
 const int kG4TapOdd[G4_NUM_TAPSETS] = {0, 0, 1, 1, 0, 1, 0, 0, 1, 1, 0};
 
+void scale_taps_by_ratio(const float* src, const float* num, const float* den, int n, float* dst)
+{
+    int k = 0;
+    for (int i = 1; i < n; ++i)
+        if (std::fabs(den[i]) > std::fabs(den[k])) k = i;
+    const double ratio = den[k] != 0.f ? (double)num[k] / (double)den[k] : 0.0;
+    for (int i = 0; i < n; ++i) dst[i] = (float)((double)src[i] * ratio);
+}
+
 void make_taps_g2(int which, int width, float spacing, float* dst) { sample(kG2[which], width, spacing, dst); }
 void make_taps_g4(int which, int width, float spacing, float* dst) { sample(kG4[which], width, spacing, dst); }
 

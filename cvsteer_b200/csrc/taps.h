@@ -13,6 +13,11 @@ enum { G2_NUM_TAPSETS = 7, G4_NUM_TAPSETS = 11, MAX_WIDTH = 32, MAX_TAPS = 2 * M
 void make_taps_g2(int which, int width, float spacing, float* dst);
 void make_taps_g4(int which, int width, float spacing, float* dst);
 
+// dst[i] = src[i] * (num[k] / den[k]) for the k with the largest |den[k]|, evaluated in double and rounded once.
+// Used where two tap functions are the same function up to a constant (g3 = sqrt(1.843) h3 in the G2 family,
+// g4 = 1.246 h4 in the G4 family), so that one row pass can serve both.
+void scale_taps_by_ratio(const float* src, const float* num, const float* den, int n, float* dst);
+
 // parity of each tap set: 0 = even (f[-i]==f[i]), 1 = odd (f[-i]==-f[i], f[0]==0); exact in fp32.
 extern const int kG2TapOdd[G2_NUM_TAPSETS];
 extern const int kG4TapOdd[G4_NUM_TAPSETS];

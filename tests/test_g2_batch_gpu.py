@@ -94,7 +94,7 @@ def test_tma_and_ldg_loaders_agree_bitwise():
     g = G2Batch()
     x = torch.from_numpy(fr).cuda()
     a = g.run(x, capi.G2_MASK_STATE)
-    assert g.last_launch()["kernel"].endswith("/tma")
+    assert "/tma" in g.last_launch()["kernel"]
     pad = torch.zeros((2, 150, 263), dtype=torch.float32, device="cuda")
     pad[:, :, 1:261] = x
     b = g.run(pad[:, :, 1:261], capi.G2_MASK_STATE)   # misaligned base + pitch: TMA cannot describe it
