@@ -187,3 +187,27 @@ def test_pyr_down_edge_sizes(shape):
     want = ref.pyr_down(img)
     assert out.shape == want.shape
     assert float(np.max(np.abs(out - want))) <= 1e-4 * 255
+
+
+def test_band_pyramid_equals_whole_bitwise():
+    """The row-band pipeline of cvsteer_b200.multi (bands + halos through a 4-level pyramid, band-mode pyr_down and
+    band-mode fused kernel) reproduces the whole-image pyramid result exactly.  Ranks are emulated sequentially."""
+    from cvsteer_b200 import multi
+    H, W, L = 400, 300, 4
+    img = synth(3800, H, W)
+    x = torch.from_numpy(img[None]).cuda()
+    g = G2Batch()
+    whole = g.run_pyramid(x, L, capi.G2_MASK_FULL)
+    process, down, _ = multi.cuda_callables(capi.G2_MASK_FULL)
+    for world in (2, 3):
+        for plan in multi.plan_bands(H, world, L):
+            if plan.empty:
+                continue
+            buf = x[0, plan.have[0][0]:plan.have[0][1]].contiguous()
+            for l in range(L):
+                res = process(buf, l, plan)
+                lo, hi = plan.out[l]
+                for k, v in res.items():
+                    assert torch.equal(v, whole[l][k][0, lo:hi]), (world, plan.rank, l, k)
+                if l + 1 < L:
+                    buf = down(buf, l, plan)
