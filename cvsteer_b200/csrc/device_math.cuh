@@ -43,7 +43,9 @@ __device__ __forceinline__ float fast_sqrt(float x)
 // min/max, evaluated with FMAs as OpenCV's SIMD path does.  With FAST = false (IEEE division) this is
 // bit-identical to cv2 4.13.0 on 2M random points; FAST = true replaces the division by MUFU.RCP (<= 2 ulp on
 // the ratio, i.e. ~1e-7 rad).
-template <bool FAST = false>
+// NANS = false skips forcing NaN inputs through (fmaxf/fminf drop NaNs); callers that need cv::patchNaNs semantics
+// test the inputs themselves (one unordered compare).
+template <bool FAST = false, bool NANS = true>
 __device__ __forceinline__ float cv_atan2(float y, float x)
 {
     constexpr float kDeg = 57.29577951308232f;  // (float)(180/CV_PI)
@@ -61,7 +63,7 @@ __device__ __forceinline__ float cv_atan2(float y, float x)
     a = (x < 0.f) ? 180.f - a : a;
     a = (y < 0.f) ? 360.f - a : a;
     // NaN inputs: fmaxf/fminf drop NaNs, so force the NaN through as cv does (c = NaN there)
-    a = (x != x || y != y) ? __int_as_float(0x7fc00000) : a;
+    if (NANS) a = (x != x || y != y) ? __int_as_float(0x7fc00000) : a;
     return a * 0.017453292519943295f;  // (float)(CV_PI/180)
 }
 
@@ -110,7 +112,7 @@ __device__ __forceinline__ Orientation orientation_g2(float a, float b, float c,
     o.c2 = c2;
     o.c3 = c3;
     o.strength = cv_magnitude<FAST>(c2, c3);
-    o.theta = 0.5f * wrap_pi(cv_atan2<FAST>(c3, c2));
+    o.theta = 0.5f * wrap_pi(cv_atan2<FAST, !FAST>(c3, c2));
     return o;
 }
 
@@ -140,8 +142,10 @@ template <bool FAST = false>
 __device__ __forceinline__ void magnitude_phase(float g, float h, float& mag, float& phase)
 {
     mag = cv_magnitude<FAST>(g, h);
-    float p = wrap_pi(cv_atan2<FAST>(h, g));
-    phase = (p != p) ? 0.f : p;  // cv::patchNaNs
+    const float p = wrap_pi(cv_atan2<FAST, false>(h, g));
+    // cv::patchNaNs: the reference's angle is NaN iff an input is NaN.  One unordered compare of the two inputs
+    // (setp.nan is true when either operand is NaN) selects 0.
+    asm("{\n\t.reg .pred q;\n\tsetp.nan.f32 q, %1, %2;\n\tselp.f32 %0, 0f00000000, %3, q;\n\t}" : "=f"(phase) : "f"(g), "f"(h), "f"(p));
 }
 
 // G2.cpp:179-186: lambda = cos^2(err) gated at pi/2.

@@ -18,7 +18,7 @@ namespace cvs {
 #define CVS_G2_MIN_CTAS 4
 #endif
 struct G2Fam {
-    static constexpr int R = 4, NSETS = 6, NROW = 5, NBASIS = 7, BH = CVS_G2_BH, MIN_CTAS = CVS_G2_MIN_CTAS;
+    static constexpr int R = 4, NSETS = 6, NROW = 5, NBASIS = 7, NPLANES = CVS_G2_NPLANES, BH = CVS_G2_BH, MIN_CTAS = CVS_G2_MIN_CTAS;
     // unique tap sets: 0 g1, 1 g2(=h2), 2 g3, 3 h1, 4 h3, 5 h4   (index into TapTable::t)
     // map from the API's 7 tap sets (g1,g2,g3,h1,h2,h3,h4) to unique sets
     __host__ __device__ static constexpr int unique_of(int api) { constexpr int t[7] = {0, 1, 2, 3, 1, 4, 5}; return t[api]; }
@@ -48,16 +48,13 @@ struct G2Fam {
     // Fused epilogue on the 7 basis values of one pixel.  MASK != 0: compile-time plane set, steering at the
     // in-kernel dominant angle, SFU approximations for 1/x, sqrt and sin/cos (all far inside the 1e-4-of-range /
     // 1e-3 rad parity budget).  MASK == 0: run-time mask and steer source, accurate sincosf for arbitrary angles.
-    // `row_off` is warp-uniform (frame + row byte offset); stores are predicated on `xin`, nothing else diverges.
-    template <unsigned MASK>
-    __device__ __forceinline__ static void epilogue(const float (&b)[NBASIS], const MarchArgs& a, long long row_off, int x, bool xin)
+    // Nothing in here diverges: there is no bounds predicate (out-of-range threads are clamped onto a valid column).
+    template <unsigned MASK, class Cursor>
+    __device__ __forceinline__ static void epilogue(const float (&b)[NBASIS], const MarchArgs& a, const Cursor& cur)
     {
         constexpr bool FAST = MASK != 0;
         const unsigned m = MASK ? MASK : a.mask;
-        const long long off = row_off + 4ll * x;  // one per-thread byte offset shared by every plane
-        auto put = [&](int p, float v) {
-            if (xin) *reinterpret_cast<float*>(reinterpret_cast<char*>(a.out[p]) + off) = v;
-        };
+        auto put = [&](int p, float v) { cur.put(a, p, v); };
 #pragma unroll
         for (int q = 0; q < NBASIS; ++q)
             if (m & (1u << q)) put(q, b[q]);
@@ -89,7 +86,7 @@ struct G2Fam {
                 ct = a.cos_t;
                 st = a.sin_t;
             } else {
-                sincosf(*reinterpret_cast<const float*>(reinterpret_cast<const char*>(a.theta_map) + (xin ? off : row_off)), &st, &ct);
+                sincosf(cur.theta(a), &st, &ct);
             }
             // cos 2t = c^2 - s^2, sin 2t = 2cs  (reference: polarToCart(2*theta), G2.cpp:175)
             if (m & CVS_BIT(CVS_E)) put(CVS_E, fmaf(o.c2, fmaf(ct, ct, -st * st), fmaf(o.c3, 2.f * ct * st, o.c1)));
@@ -119,7 +116,7 @@ struct G2Fam {
 #define CVS_G4_MIN_CTAS 2
 #endif
 struct G4Fam {
-    static constexpr int R = 6, NSETS = 11, NROW = 9, NBASIS = 11, BH = CVS_G4_BH, MIN_CTAS = CVS_G4_MIN_CTAS;
+    static constexpr int R = 6, NSETS = 11, NROW = 9, NBASIS = 11, NPLANES = CVS_G4_NPLANES, BH = CVS_G4_BH, MIN_CTAS = CVS_G4_MIN_CTAS;
     // tap table rows: 0 g1, 1 g2(=h2), 2 g3, 3 g4, 4 g5, 5 h1, 6 h3, 7 h4, 8 h5, 9 h6, 10 g3 * (g4/h4)
     // API order g1..g5,h1..h6
     __host__ __device__ static constexpr int unique_of(int api) { constexpr int t[11] = {0, 1, 2, 3, 4, 5, 1, 6, 7, 8, 9}; return t[api]; }
@@ -142,15 +139,12 @@ struct G4Fam {
     static constexpr unsigned kNeedsSteer = CVS_G4_MASK_STEER;
 
     // MASK != 0: compile-time plane set, steering at a per-pixel angle map (config 4), SFU approximations.
-    template <unsigned MASK>
-    __device__ __forceinline__ static void epilogue(const float (&b)[NBASIS], const MarchArgs& a, long long row_off, int x, bool xin)
+    template <unsigned MASK, class Cursor>
+    __device__ __forceinline__ static void epilogue(const float (&b)[NBASIS], const MarchArgs& a, const Cursor& cur)
     {
         constexpr bool FAST = MASK != 0;
         const unsigned m = MASK ? MASK : a.mask;
-        const long long off = row_off + 4ll * x;  // one per-thread byte offset shared by every plane
-        auto put = [&](int p, float v) {
-            if (xin) *reinterpret_cast<float*>(reinterpret_cast<char*>(a.out[p]) + off) = v;
-        };
+        auto put = [&](int p, float v) { cur.put(a, p, v); };
 #pragma unroll
         for (int q = 0; q < NBASIS; ++q)
             if (m & (1u << q)) put(q, b[q]);
@@ -160,7 +154,7 @@ struct G4Fam {
             ct = a.cos_t;
             st = a.sin_t;
         } else {
-            sincosf(*reinterpret_cast<const float*>(reinterpret_cast<const char*>(a.theta_map) + (xin ? off : row_off)), &st, &ct);
+            sincosf(cur.theta(a), &st, &ct);
         }
         float g4, h4;
         dev::steer_g4(ct, st, &b[0], &b[5], g4, h4);

@@ -68,7 +68,8 @@ __global__ void k_generic_cols(const __grid_constant__ MarchArgs a, const __grid
         for (int q = 0; q < Fam::NBASIS; ++q) b[q] = fmaf(taps.t[Fam::basis_set(q)][i + w], v[Fam::basis_row(q)], b[q]);
     }
     const long long row_off = (long long)frame * a.out_frame_stride + (long long)(y - a.out_row_origin) * a.out_pitch;
-    Fam::template epilogue<0>(b, a, row_off, x, true);
+    const OutCursor<0u, Fam::NPLANES> cur(a, row_off, x);
+    Fam::template epilogue<0>(b, a, cur);
 }
 
 template <class Fam>

@@ -102,6 +102,66 @@ struct TapTable {
 };
 
 // ------------------------------------------------------------------------------------------------
+// Output cursor: where this thread's pixel of the current row lives in every output plane.
+// ------------------------------------------------------------------------------------------------
+// Static masks: every selected plane keeps a loop-invariant 64-bit base (band origin of this CTA) in a vector register
+// pair, and ONE 32-bit element index per thread walks down the band.  A store is then IMAD.WIDE.U32 (idx*4 + base) +
+// STG: 2 issue slots instead of the 4 a 64-bit add pair per plane costs.  The bases are laundered through an opaque
+// `mov` so that ptxas keeps them in vector registers (as a uniform-register value they could not be the addend of
+// IMAD.WIDE); the index stays far below 2^32 because it is relative to the CTA's own band (<= BH rows).
+__device__ __forceinline__ unsigned long long opaque64(unsigned long long v)
+{
+    unsigned long long r;
+    asm volatile("mov.b64 %0, %1;" : "=l"(r) : "l"(v));
+    return r;
+}
+
+template <unsigned MASK, int NPLANES>
+struct OutCursor {
+    unsigned long long base[NPLANES];
+    unsigned long long th_base;  // steering-angle map (same layout as the outputs); dead unless theta() is used
+    unsigned idx;                // element index of this thread's pixel relative to the bases
+    unsigned pitch_elems;
+    __device__ __forceinline__ OutCursor(const MarchArgs& a, long long band_off, int x)
+    {
+#pragma unroll
+        for (int q = 0; q < NPLANES; ++q)
+            base[q] = (MASK >> q & 1u) ? opaque64((unsigned long long)(reinterpret_cast<char*>(a.out[q]) + band_off)) : 0ull;
+        th_base = opaque64((unsigned long long)(reinterpret_cast<const char*>(a.theta_map) + band_off));
+        idx = (unsigned)x;
+        pitch_elems = (unsigned)(a.out_pitch >> 2);
+    }
+    // No predicate: threads past the right image edge are clamped onto the last valid column (see k_march), so they
+    // recompute that pixel and store the identical value to the identical address.
+    __device__ __forceinline__ void put(const MarchArgs&, int q, float v) const
+    {
+        asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %1, 4, %0;\n\tst.global.f32 [a], %2;\n\t}" ::"l"(base[q]), "r"(idx), "f"(v) : "memory");
+    }
+    __device__ __forceinline__ float theta(const MarchArgs&) const
+    {
+        float v;
+        asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %2, 4, %1;\n\tld.global.nc.f32 %0, [a];\n\t}" : "=f"(v) : "l"(th_base), "r"(idx));
+        return v;
+    }
+    __device__ __forceinline__ void next_row() { idx += pitch_elems; }
+};
+
+template <int NPLANES>
+struct OutCursor<0u, NPLANES> {  // run-time mask: one shared byte offset, 64-bit add per plane at the store
+    long long off, pitch;
+    __device__ __forceinline__ OutCursor(const MarchArgs& a, long long band_off, int x) : off(band_off + 4ll * x), pitch(a.out_pitch) {}
+    __device__ __forceinline__ void put(const MarchArgs& a, int q, float v) const
+    {
+        *reinterpret_cast<float*>(reinterpret_cast<char*>(a.out[q]) + off) = v;
+    }
+    __device__ __forceinline__ float theta(const MarchArgs& a) const
+    {
+        return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(a.theta_map) + off);
+    }
+    __device__ __forceinline__ void next_row() { off += pitch; }
+};
+
+// ------------------------------------------------------------------------------------------------
 // Tile loaders
 // ------------------------------------------------------------------------------------------------
 // Patch BORDER_REFLECT_101 halos of a TMA-loaded (zero-filled) tile in place.  Requires cols >= R+1 and
@@ -199,9 +259,10 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
         load_tile_manual<R, TWH, TROWS, TIn>(tile, a, frame, x0, ytop, TW);
     }
 
-    const int x = x0 + threadIdx.x;
-    const bool xin = x < a.cols;
-    const float* tcol = tile + threadIdx.x + (march_halo_left(R) - R);  // leftmost tap of this thread's column
+    // Threads past the right image edge (ragged last strip) are clamped onto the last valid column: they redo that pixel
+    // and store the same value to the same address, so the loop needs no bounds predicate at all.
+    const int x = min(x0 + (int)threadIdx.x, a.cols - 1);
+    const float* tcol = tile + (x - x0) + (march_halo_left(R) - R);  // leftmost tap of this thread's column
     int nrows = a.out_row_end - yb;
     nrows = nrows < BH ? nrows : BH;
 
@@ -271,7 +332,9 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
     // The window rotates by one slot per row.  Register files cannot be indexed dynamically, so the row/column code
     // exists once per slot (a K-way switch); everything that does not depend on the slot -- the whole point-wise
     // epilogue -- follows the switch ONCE, which keeps the loop body inside the instruction cache.
-    long long row_off = (long long)frame * a.out_frame_stride + (long long)(yb - a.out_row_origin) * a.out_pitch;
+    // Output addressing: see OutCursor.
+    const long long band_off = (long long)frame * a.out_frame_stride + (long long)(yb - a.out_row_origin) * a.out_pitch;
+    OutCursor<MASK, Fam::NPLANES> cur(a, band_off, x);
     int slot = 0;
 #pragma unroll 1
     for (int rt = 0; rt < nrows + 2 * R; ++rt) {
@@ -287,8 +350,8 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
         }
         slot = (slot + 1 == K) ? 0 : slot + 1;
         if (rt >= 2 * R) {
-            Fam::template epilogue<MASK>(b, a, row_off, x, xin);
-            row_off += a.out_pitch;
+            Fam::template epilogue<MASK>(b, a, cur);
+            cur.next_row();
         }
     }
 }
