@@ -11,6 +11,12 @@
 
 namespace cvs {
 
+#ifndef CVS_G2_SHARED_ROW
+#define CVS_G2_SHARED_ROW false
+#endif
+#ifndef CVS_G4_SHARED_ROW
+#define CVS_G4_SHARED_ROW true
+#endif
 #ifndef CVS_G2_BH
 #define CVS_G2_BH 64
 #endif
@@ -19,6 +25,7 @@ namespace cvs {
 #endif
 struct G2Fam {
     static constexpr int R = 4, NSETS = 6, NROW = 5, NBASIS = 7, NPLANES = CVS_G2_NPLANES, BH = CVS_G2_BH, MIN_CTAS = CVS_G2_MIN_CTAS;
+    static constexpr bool SHARED_ROW_PASS = CVS_G2_SHARED_ROW;
     // unique tap sets: 0 g1, 1 g2(=h2), 2 g3, 3 h1, 4 h3, 5 h4   (index into TapTable::t)
     // map from the API's 7 tap sets (g1,g2,g3,h1,h2,h3,h4) to unique sets
     __host__ __device__ static constexpr int unique_of(int api) { constexpr int t[7] = {0, 1, 2, 3, 1, 4, 5}; return t[api]; }
@@ -41,6 +48,13 @@ struct G2Fam {
     static constexpr int kBakedWidth = CVS_BAKED_G2_WIDTH;
     __host__ __device__ static constexpr float baked(int set, int i) { constexpr float t[NSETS][R + 1] = CVS_BAKED_G2_TAPS; return t[set][i]; }
 
+    // does this launch read the per-pixel steering-angle map?  (static masks always steer at the in-kernel theta_d)
+    template <unsigned MASK>
+    __device__ __forceinline__ static bool reads_theta_map(const MarchArgs& a)
+    {
+        return MASK == 0 && a.steer_source == CVS_STEER_MAP && (a.mask & (kNeedsSteer | CVS_BIT(CVS_E)));
+    }
+
     static constexpr unsigned kNeedsOrient = 0x000FFF80u;   // anything beyond the 7 basis planes
     static constexpr unsigned kNeedsSteer = CVS_BIT(CVS_G2T) | CVS_BIT(CVS_H2T) | CVS_BIT(CVS_MAG) | CVS_BIT(CVS_PHASE) |
                                             CVS_BIT(CVS_EDGES) | CVS_BIT(CVS_DARK) | CVS_BIT(CVS_BRIGHT);
@@ -50,7 +64,7 @@ struct G2Fam {
     // 1e-3 rad parity budget).  MASK == 0: run-time mask and steer source, accurate sincosf for arbitrary angles.
     // Nothing in here diverges: there is no bounds predicate (out-of-range threads are clamped onto a valid column).
     template <unsigned MASK, class Cursor>
-    __device__ __forceinline__ static void epilogue(const float (&b)[NBASIS], const MarchArgs& a, const Cursor& cur)
+    __device__ __forceinline__ static void epilogue(const float (&b)[NBASIS], const MarchArgs& a, const Cursor& cur, float theta_px)
     {
         constexpr bool FAST = MASK != 0;
         const unsigned m = MASK ? MASK : a.mask;
@@ -86,7 +100,7 @@ struct G2Fam {
                 ct = a.cos_t;
                 st = a.sin_t;
             } else {
-                sincosf(cur.theta(a), &st, &ct);
+                sincosf(theta_px, &st, &ct);
             }
             // cos 2t = c^2 - s^2, sin 2t = 2cs  (reference: polarToCart(2*theta), G2.cpp:175)
             if (m & CVS_BIT(CVS_E)) put(CVS_E, fmaf(o.c2, fmaf(ct, ct, -st * st), fmaf(o.c3, 2.f * ct * st, o.c1)));
@@ -117,6 +131,7 @@ struct G2Fam {
 #endif
 struct G4Fam {
     static constexpr int R = 6, NSETS = 11, NROW = 9, NBASIS = 11, NPLANES = CVS_G4_NPLANES, BH = CVS_G4_BH, MIN_CTAS = CVS_G4_MIN_CTAS;
+    static constexpr bool SHARED_ROW_PASS = CVS_G4_SHARED_ROW;
     // tap table rows: 0 g1, 1 g2(=h2), 2 g3, 3 g4, 4 g5, 5 h1, 6 h3, 7 h4, 8 h5, 9 h6, 10 g3 * (g4/h4)
     // API order g1..g5,h1..h6
     __host__ __device__ static constexpr int unique_of(int api) { constexpr int t[11] = {0, 1, 2, 3, 4, 5, 1, 6, 7, 8, 9}; return t[api]; }
@@ -137,10 +152,16 @@ struct G4Fam {
     __host__ __device__ static constexpr float baked(int set, int i) { constexpr float t[NSETS][R + 1] = CVS_BAKED_G4_TAPS; return t[set][i]; }
 
     static constexpr unsigned kNeedsSteer = CVS_G4_MASK_STEER;
+    // static steer masks are only dispatched for map steering (march_g4.cu)
+    template <unsigned MASK>
+    __device__ __forceinline__ static bool reads_theta_map(const MarchArgs& a)
+    {
+        return MASK ? (MASK & kNeedsSteer) != 0 : (a.steer_source == CVS_STEER_MAP && (a.mask & kNeedsSteer));
+    }
 
     // MASK != 0: compile-time plane set, steering at a per-pixel angle map (config 4), SFU approximations.
     template <unsigned MASK, class Cursor>
-    __device__ __forceinline__ static void epilogue(const float (&b)[NBASIS], const MarchArgs& a, const Cursor& cur)
+    __device__ __forceinline__ static void epilogue(const float (&b)[NBASIS], const MarchArgs& a, const Cursor& cur, float theta_px)
     {
         constexpr bool FAST = MASK != 0;
         const unsigned m = MASK ? MASK : a.mask;
@@ -154,7 +175,7 @@ struct G4Fam {
             ct = a.cos_t;
             st = a.sin_t;
         } else {
-            sincosf(cur.theta(a), &st, &ct);
+            sincosf(theta_px, &st, &ct);
         }
         float g4, h4;
         dev::steer_g4(ct, st, &b[0], &b[5], g4, h4);

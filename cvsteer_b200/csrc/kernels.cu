@@ -69,7 +69,7 @@ __global__ void k_generic_cols(const __grid_constant__ MarchArgs a, const __grid
     }
     const long long row_off = (long long)frame * a.out_frame_stride + (long long)(y - a.out_row_origin) * a.out_pitch;
     const OutCursor<0u, Fam::NPLANES> cur(a, row_off, x);
-    Fam::template epilogue<0>(b, a, cur);
+    Fam::template epilogue<0>(b, a, cur, Fam::template reads_theta_map<0>(a) ? cur.theta(a) : 0.f);
 }
 
 template <class Fam>

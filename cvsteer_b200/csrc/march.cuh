@@ -276,10 +276,10 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
     float win[NROW][K];  // (2R+1)-row register window per row-filtered plane; slot indices are compile-time
     float b[NB];
 
-    // One tile row: all unique row passes into window slot `slot`; then, once the window is full, all column passes.
-    // Even/odd symmetry: R sums + R differences are shared by every filter of the pass.
-    auto row_col = [&](int rt, auto slot_c) {
-        constexpr int slot = decltype(slot_c)::value;
+    // One tile row: all unique row passes (even/odd symmetry: R sums + R differences are shared by every filter of the
+    // pass), results in r[].
+    float r[NROW];
+    auto row_pass = [&](int rt) {
         const float* src = tcol + rt * TWH;
         float v[K];
 #pragma unroll
@@ -305,43 +305,59 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
 #pragma unroll
                 for (int i = 1; i <= R; ++i) acc = fmaf(tap(set, i), s[i], acc);
             }
-            win[p][slot] = acc;
+            r[p] = acc;
         }
-        if (rt >= 2 * R) {  // CTA-uniform: the first 2R rows only feed the window
-            constexpr int ctr = (slot + K - R) % K;  // slot of the centre row
+    };
+    // Column passes for the window whose NEWEST row is r[] (not yet stored) and whose oldest row still sits in `slot`;
+    // afterwards r[] takes the oldest row's place.  Row offset k in [-R, R] around the centre row lives in slot
+    // (slot + 1 + R + k) mod K for k < R, and in r[] for k == R.
+    auto col_pass = [&](bool emit, auto slot_c) {
+        constexpr int slot = decltype(slot_c)::value;
+        if (emit) {  // CTA-uniform: the first 2R rows only feed the window
 #pragma unroll
             for (int q = 0; q < NB; ++q) {
                 const int rp = Fam::basis_row(q), set = Fam::basis_set(q);
+                auto w = [&](int k) -> float { return k == R ? r[rp] : win[rp][(slot + 1 + R + k + K) % K]; };
                 float acc;
                 if (Fam::basis_odd(q)) {
-                    acc = tap(set, 1) * (win[rp][(ctr + 1) % K] - win[rp][(ctr + K - 1) % K]);
+                    acc = tap(set, 1) * (w(1) - w(-1));
 #pragma unroll
-                    for (int i = 2; i <= R; ++i)
-                        acc = fmaf(tap(set, i), win[rp][(ctr + i) % K] - win[rp][(ctr + K - i) % K], acc);
+                    for (int i = 2; i <= R; ++i) acc = fmaf(tap(set, i), w(i) - w(-i), acc);
                 } else {
-                    acc = tap(set, 0) * win[rp][ctr];
+                    acc = tap(set, 0) * w(0);
 #pragma unroll
-                    for (int i = 1; i <= R; ++i)
-                        acc = fmaf(tap(set, i), win[rp][(ctr + i) % K] + win[rp][(ctr + K - i) % K], acc);
+                    for (int i = 1; i <= R; ++i) acc = fmaf(tap(set, i), w(i) + w(-i), acc);
                 }
                 b[q] = acc;
             }
         }
+#pragma unroll
+        for (int p = 0; p < NROW; ++p) win[p][slot] = r[p];
     };
 
-    // The window rotates by one slot per row.  Register files cannot be indexed dynamically, so the row/column code
-    // exists once per slot (a K-way switch); everything that does not depend on the slot -- the whole point-wise
-    // epilogue -- follows the switch ONCE, which keeps the loop body inside the instruction cache.
+    // The window rotates by one slot per row.  Register files cannot be indexed dynamically, so the slot-dependent code
+    // exists once per slot behind a K-way switch.  Everything that does not depend on the slot follows the switch ONCE
+    // (the whole point-wise epilogue) or, for families with Fam::SHARED_ROW_PASS, precedes it once (the row pass, at
+    // the price of NROW register moves per row): this is what keeps the loop body inside the instruction cache.
     // Output addressing: see OutCursor.
     const long long band_off = (long long)frame * a.out_frame_stride + (long long)(yb - a.out_row_origin) * a.out_pitch;
-    OutCursor<MASK, Fam::NPLANES> cur(a, band_off, x);
+    // per-plane base registers only pay off while there are few planes (2 registers each); wide masks share one offset
+    OutCursor<(__builtin_popcount(MASK) <= 8 ? MASK : 0u), Fam::NPLANES> cur(a, band_off, x);
     int slot = 0;
 #pragma unroll 1
     for (int rt = 0; rt < nrows + 2 * R; ++rt) {
+        // steering-angle map: issue the load for this output row before ~all of the row's arithmetic, so that its DRAM
+        // latency is covered by the row/column passes instead of stalling the epilogue
+        float theta_px = 0.f;
+        if (Fam::template reads_theta_map<MASK>(a) && rt >= 2 * R) theta_px = cur.theta(a);
+        if constexpr (Fam::SHARED_ROW_PASS) row_pass(rt);
         switch (slot) {
-#define CVS_CASE(I)                                          \
-    case I:                                                  \
-        if constexpr (I < K) row_col(rt, std::integral_constant<int, (I < K ? I : 0)>{}); \
+#define CVS_CASE(I)                                                        \
+    case I:                                                                \
+        if constexpr (I < K) {                                             \
+            if constexpr (!Fam::SHARED_ROW_PASS) row_pass(rt);             \
+            col_pass(rt >= 2 * R, std::integral_constant<int, (I < K ? I : 0)>{}); \
+        }                                                                  \
         break;
             CVS_CASE(0) CVS_CASE(1) CVS_CASE(2) CVS_CASE(3) CVS_CASE(4) CVS_CASE(5) CVS_CASE(6) CVS_CASE(7) CVS_CASE(8)
             CVS_CASE(9) CVS_CASE(10) CVS_CASE(11) CVS_CASE(12)
@@ -350,7 +366,7 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
         }
         slot = (slot + 1 == K) ? 0 : slot + 1;
         if (rt >= 2 * R) {
-            Fam::template epilogue<MASK>(b, a, cur);
+            Fam::template epilogue<MASK>(b, a, cur, theta_px);
             cur.next_row();
         }
     }

@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--cols", type=int, default=1920)
     ap.add_argument("--g4", action="store_true")
     ap.add_argument("--ffma", action="store_true")
+    ap.add_argument("--only-g4", action="store_true")
     a = ap.parse_args()
     out = {}
     if a.ffma:
@@ -40,7 +41,7 @@ def main():
     x = torch.rand((a.n, a.rows, a.cols), device="cuda") * 255
     mpix = a.n * a.rows * a.cols / 1e6
     g = G2Batch()
-    for name, mask, bpp in (("M0", capi.G2_MASK_STATE, 52), ("M1", capi.G2_MASK_ORIENT, 16), ("M2", capi.G2_MASK_FULL, 32)):
+    for name, mask, bpp in (() if a.only_g4 else (("M0", capi.G2_MASK_STATE, 52), ("M1", capi.G2_MASK_ORIENT, 16), ("M2", capi.G2_MASK_FULL, 32))):
         outs = {p: torch.empty((a.n, a.rows, a.cols), device="cuda") for p in range(capi.G2_NPLANES) if mask >> p & 1}
         ms = time_ms(lambda: g.run(x, mask, outs=outs))
         out[name] = {"ms": round(ms, 4), "Gpix_s": round(mpix / ms, 2), "GB_s": round(mpix * bpp / ms, 1), "k": g.last_launch()["kernel"]}
