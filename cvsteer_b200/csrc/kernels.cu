@@ -4,6 +4,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <utility>
@@ -315,6 +316,80 @@ __global__ void k_pyr_down(const __grid_constant__ MarchArgs a, float* out, int 
                               (long long)(yo - a.out_row_origin) * a.out_pitch + 4ll * xo) = v;
 }
 
+// Fast path (fp32): one thread per OUTPUT column marching down PD_ROWS output rows.  Per input row a thread reads its
+// five taps as two aligned float2 + one float (columns 2xo-2 .. 2xo+2), reduces them horizontally, and keeps a 5-row
+// register window of the horizontal results; every second input row it emits one output.  All loads of an iteration
+// (4 input rows = 2 outputs) are issued before any arithmetic so that ~80 B per thread are in flight: the kernel is
+// HBM-bound (reads every input pixel once, writes a quarter).  Same arithmetic order as k_pyr_down.
+enum { PD_ROWS = 32, PD_THREADS = 128 };
+
+__global__ void __launch_bounds__(PD_THREADS) k_pyr_down_march(const __grid_constant__ MarchArgs a, float* out, int out_cols)
+{
+    const int xo = blockIdx.x * PD_THREADS + threadIdx.x;
+    const int frame = blockIdx.z;
+    if (xo >= out_cols) return;
+    const int yo0 = a.out_row_begin + blockIdx.y * PD_ROWS;
+    const int yo1 = min(yo0 + PD_ROWS, a.out_row_end);
+    const char* base = reinterpret_cast<const char*>(a.in) + (long long)frame * a.in_frame_stride;
+    const int xc = 2 * xo;
+    const bool interior = (xc - 2 >= 0) && (xc + 2 < a.cols);  // vector path; image-edge columns take the reflect path
+    int xs0 = 0, xs1 = 0, xs3 = 0, xs4 = 0;
+    if (!interior) {
+        xs0 = dev::reflect101(xc - 2, a.cols), xs1 = dev::reflect101(xc - 1, a.cols);
+        xs3 = dev::reflect101(xc + 1, a.cols), xs4 = dev::reflect101(xc + 2, a.cols);
+    }
+    // horizontal 5-tap of image row y (reflected), OpenCV order: 6*c + 4*(l1+r1) + l2 + r2
+    auto load_row = [&](int y, float2& p, float2& q, float& e) {
+        const int gy = dev::reflect101(y, a.full_rows) - a.y_origin;
+        const float* src = reinterpret_cast<const float*>(base + (long long)gy * a.in_pitch);
+        if (interior) {
+            p = *reinterpret_cast<const float2*>(src + xc - 2);
+            q = *reinterpret_cast<const float2*>(src + xc);
+            e = src[xc + 2];
+        } else {
+            p = make_float2(src[xs0], src[xs1]);
+            q = make_float2(src[xc], src[xs3]);
+            e = src[xs4];
+        }
+    };
+    auto hsum = [](const float2& p, const float2& q, float e) { return q.x * 6.f + (p.y + q.y) * 4.f + p.x + e; };
+    float h0, h1, h2, h3, h4;
+    {
+        float2 p0, q0, p1, q1, p2, q2;
+        float e0, e1, e2;
+        load_row(2 * yo0 - 2, p0, q0, e0);
+        load_row(2 * yo0 - 1, p1, q1, e1);
+        load_row(2 * yo0, p2, q2, e2);
+        h0 = hsum(p0, q0, e0), h1 = hsum(p1, q1, e1), h2 = hsum(p2, q2, e2);
+    }
+    float* dst = reinterpret_cast<float*>(reinterpret_cast<char*>(out) + (long long)frame * a.out_frame_stride +
+                                          (long long)(yo0 - a.out_row_origin) * a.out_pitch) + xo;
+    const long long opitch = a.out_pitch >> 2;
+    int yo = yo0;
+    for (; yo + 1 < yo1; yo += 2) {
+        float2 p3, q3, p4, q4, p5, q5, p6, q6;
+        float e3, e4, e5, e6;
+        load_row(2 * yo + 1, p3, q3, e3);
+        load_row(2 * yo + 2, p4, q4, e4);
+        load_row(2 * yo + 3, p5, q5, e5);
+        load_row(2 * yo + 4, p6, q6, e6);
+        h3 = hsum(p3, q3, e3), h4 = hsum(p4, q4, e4);
+        const float h5 = hsum(p5, q5, e5), h6 = hsum(p6, q6, e6);
+        dst[0] = (h2 * 6.f + (h1 + h3) * 4.f + h0 + h4) * (1.f / 256.f);
+        dst[opitch] = (h4 * 6.f + (h3 + h5) * 4.f + h2 + h6) * (1.f / 256.f);
+        dst += 2 * opitch;
+        h0 = h4, h1 = h5, h2 = h6;
+    }
+    if (yo < yo1) {
+        float2 p3, q3, p4, q4;
+        float e3, e4;
+        load_row(2 * yo + 1, p3, q3, e3);
+        load_row(2 * yo + 2, p4, q4, e4);
+        h3 = hsum(p3, q3, e3), h4 = hsum(p4, q4, e4);
+        dst[0] = (h2 * 6.f + (h1 + h3) * 4.f + h0 + h4) * (1.f / 256.f);
+    }
+}
+
 cudaError_t launch_pyr_down(const BatchGeom& g, float* out, cudaStream_t stream)
 {
     SteerSpec st{};
@@ -323,7 +398,13 @@ cudaError_t launch_pyr_down(const BatchGeom& g, float* out, cudaStream_t stream)
     const int out_rows = g.out_row_end - g.out_row_begin;
     if (out_rows <= 0 || g.n <= 0 || g.n > 65535) return cudaErrorInvalidValue;
     const dim3 grid((out_cols + 127) / 128, out_rows, g.n);
-    if (g.in_u8)
+    static const bool force_simple = getenv("CVS_PYR_SIMPLE") != nullptr;
+    // float2 loads need 8-byte aligned rows; every output pitch must be a multiple of 4 bytes (it is: fp32 planes)
+    const bool vec_ok = !g.in_u8 && !force_simple && (((uintptr_t)g.in | g.in_pitch | g.in_frame_stride) & 7) == 0;
+    if (vec_ok)
+        k_pyr_down_march<<<dim3((out_cols + PD_THREADS - 1) / PD_THREADS, (out_rows + PD_ROWS - 1) / PD_ROWS, g.n), PD_THREADS, 0, stream>>>(
+            a, out, out_cols);
+    else if (g.in_u8)
         k_pyr_down<unsigned char><<<grid, 128, 0, stream>>>(a, out, out_cols);
     else
         k_pyr_down<float><<<grid, 128, 0, stream>>>(a, out, out_cols);
