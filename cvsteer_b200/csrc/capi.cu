@@ -7,7 +7,10 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <new>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/cvsteer_c.h"
@@ -634,6 +637,39 @@ extern "C" int cvs_g2_run_batch_host(cvs_g2* h, const float* in, int n, int rows
             }
     }
     for (int i = 0; i < NBUF; ++i) CU_TRY(cudaStreamSynchronize(streams[i]));
+    return CVS_OK;
+}
+
+extern "C" int cvs_g2_run_batch_host_multi(int n_devices, const int* devices, int width, float spacing, const float* in, int n, int rows,
+                                           int cols, size_t in_step, size_t in_frame_stride, unsigned mask, float* const* outs,
+                                           size_t out_step, size_t out_frame_stride)
+{
+    if (n_devices <= 0 || n_devices > 64 || !in || !outs || n <= 0) return fail(CVS_ERR_INVALID_ARG, "bad argument");
+    const int per = (n + n_devices - 1) / n_devices;
+    std::vector<std::thread> threads;
+    std::vector<int> rc(n_devices, CVS_OK);
+    std::vector<std::string> msg(n_devices);
+    for (int d = 0; d < n_devices; ++d) {
+        const int f0 = d * per, nf = std::min(per, n - f0);
+        if (nf <= 0) break;
+        threads.emplace_back([&, d, f0, nf] {
+            cvs_g2* h = nullptr;
+            int r = cvs_g2_create(&h, devices ? devices[d] : d, width, spacing);
+            if (r == CVS_OK) {
+                float* o[CVS_G2_NPLANES];
+                for (int p = 0; p < CVS_G2_NPLANES; ++p)
+                    o[p] = outs[p] ? reinterpret_cast<float*>(reinterpret_cast<char*>(outs[p]) + (size_t)f0 * out_frame_stride) : nullptr;
+                r = cvs_g2_run_batch_host(h, reinterpret_cast<const float*>(reinterpret_cast<const char*>(in) + (size_t)f0 * in_frame_stride), nf, rows,
+                                          cols, in_step, in_frame_stride, mask, o, out_step, out_frame_stride);
+            }
+            if (r != CVS_OK) msg[d] = cvs_last_error();  // thread-local text: carry it back to the caller's thread
+            rc[d] = r;
+            cvs_g2_destroy(h);
+        });
+    }
+    for (auto& t : threads) t.join();
+    for (int d = 0; d < n_devices; ++d)
+        if (rc[d] != CVS_OK) return fail(rc[d], "device %d: %s", devices ? devices[d] : d, msg[d].c_str());
     return CVS_OK;
 }
 

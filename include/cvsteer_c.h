@@ -195,6 +195,15 @@ CVS_API int cvs_g2_run_batch_host(cvs_g2* h, const float* in, int n, int rows, i
                                   size_t in_frame_stride, unsigned mask, float* const* outs,
                                   size_t out_step, size_t out_frame_stride);
 
+/* Same call sharded by frame over `n_devices` GPUs of this process (devices[i], or 0..n-1 when devices == NULL):
+ * contiguous blocks of ceil(n/n_devices) frames, one host thread + one handle + its own streams per GPU, NO collective
+ * (frames are independent units, as the reference's cv::parallel_for_ over files is: example/steer.cpp:169).
+ * For one-process-per-GPU deployments use the per-rank calls above; cvsteer_b200/multi.py does that over
+ * torch.distributed, including the row-band mode with its NCCL gather. */
+CVS_API int cvs_g2_run_batch_host_multi(int n_devices, const int* devices, int width, float spacing, const float* in, int n,
+                                        int rows, int cols, size_t in_step, size_t in_frame_stride, unsigned mask,
+                                        float* const* outs, size_t out_step, size_t out_frame_stride);
+
 /* ---- measurement helpers (used by bench.py; not part of the reference surface) ---- */
 /* Saturating FFMA loop: returns achieved fp32 instructions/s (1 FFMA = 1 instr = 2 flop).
  * form: 0 = immediate-operand FFMA, 1 = register-operand, 2 = constant-bank operand. */

@@ -211,3 +211,58 @@ def test_band_pyramid_equals_whole_bitwise():
                     assert torch.equal(v, whole[l][k][0, lo:hi]), (world, plan.rank, l, k)
                 if l + 1 < L:
                     buf = down(buf, l, plan)
+
+
+def test_host_batch_api_matches_device_path():
+    """cvs_g2_run_batch_host (the e2e call of bench.py): chunked H2D / kernel / D2H pipeline == one device launch."""
+    fr = _frames(3900, 7, 120, 200)                      # 7 frames: uneven chunks
+    g = G2Batch()
+    dev = g.run(torch.from_numpy(fr).cuda(), capi.G2_MASK_FULL)
+    xh = torch.from_numpy(fr).pin_memory()
+    planes = [p for p in range(capi.G2_NPLANES) if capi.G2_MASK_FULL >> p & 1]
+    oh = {p: torch.empty((7, 120, 200), dtype=torch.float32).pin_memory() for p in planes}
+    g.run_host(xh, capi.G2_MASK_FULL, oh)
+    for p in planes:
+        assert torch.equal(oh[p], dev[capi.G2_PLANE_NAMES[p]].cpu()), capi.G2_PLANE_NAMES[p]
+    # pageable host memory works too (slower)
+    oh2 = {p: torch.empty((7, 120, 200), dtype=torch.float32) for p in planes}
+    g.run_host(torch.from_numpy(fr), capi.G2_MASK_FULL, oh2)
+    assert torch.equal(oh2[capi.PHASE], oh[capi.PHASE])
+
+
+def test_batch_api_errors():
+    import ctypes as C
+    g = G2Batch()
+    x = torch.zeros((1, 16, 16), device="cuda")
+    with pytest.raises(capi.CvsError) as e:
+        g.run(x, 0)
+    assert e.value.code == capi.ERR_INVALID_ARG
+    with pytest.raises(capi.CvsError):
+        g.run(x, 1 << 25)
+    with pytest.raises(capi.CvsError):
+        g.run(x, capi.G2_MASK_FULL, steer=capi.STEER_MAP)          # no theta map
+    with pytest.raises(capi.CvsError):
+        g.run(torch.zeros((1, 16, 16)), capi.G2_MASK_FULL)          # host tensor on the device path
+    b = capi.Batch()
+    assert capi.lib().cvs_g2_run_batch_dev(g._h, C.byref(b), 1, 0, 0.0, None, None, None) == capi.ERR_INVALID_ARG
+    assert b"null" in capi.lib().cvs_last_error()
+
+
+def test_multi_device_host_api():
+    """cvs_g2_run_batch_host_multi: frames sharded over every visible GPU from ONE process (threads, no collective)."""
+    import ctypes as C
+    ndev = torch.cuda.device_count()
+    fr = _frames(3950, 5, 90, 130)
+    want = G2Batch().run(torch.from_numpy(fr).cuda(), capi.G2_MASK_ORIENT)
+    planes = [p for p in range(capi.G2_NPLANES) if capi.G2_MASK_ORIENT >> p & 1]
+    outs = {p: np.empty((5, 90, 130), np.float32) for p in planes}
+    arr = (C.c_void_p * capi.G2_NPLANES)()
+    for p in planes:
+        arr[p] = outs[p].ctypes.data
+    for nd in sorted({1, ndev}):
+        for o in outs.values():
+            o.fill(0)
+        capi.check(capi.lib().cvs_g2_run_batch_host_multi(nd, None, 4, 0.67, fr.ctypes.data, 5, 90, 130, 130 * 4, 90 * 130 * 4,
+                                                          capi.G2_MASK_ORIENT, arr, 130 * 4, 90 * 130 * 4))
+        for p in planes:
+            assert np.array_equal(outs[p], want[capi.G2_PLANE_NAMES[p]].cpu().numpy()), (nd, p)
