@@ -676,7 +676,7 @@ extern "C" int cvs_g2_run_batch_host_multi(int n_devices, const int* devices, in
 // ================================ measurement helpers ================================
 extern "C" int cvs_bench_ffma(int device, int form, int iters, double* instr_per_s, float* elapsed_ms)
 {
-    if (form < 0 || form > 2 || iters <= 0 || !instr_per_s) return fail(CVS_ERR_INVALID_ARG, "bad argument");
+    if (form < 0 || form > 5 || iters <= 0 || !instr_per_s) return fail(CVS_ERR_INVALID_ARG, "bad argument");
     CU_TRY(cudaSetDevice(device));
     cudaDeviceProp prop;
     CU_TRY(cudaGetDeviceProperties(&prop, device));
@@ -696,7 +696,8 @@ extern "C" int cvs_bench_ffma(int device, int form, int iters, double* instr_per
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaFree(sink);
-    const double n = (double)blocks * threads * (double)iters * 64.0;  // 4 x 16 FFMA per iteration per thread
+    // 4 x 16 FMA instructions per iteration per thread; the packed forms (3, 4) do two lane-FMAs per instruction
+    const double n = (double)blocks * threads * (double)iters * 64.0 * ((form == 3 || form == 4) ? 2.0 : 1.0);
     *instr_per_s = n / (ms * 1e-3);
     if (elapsed_ms) *elapsed_ms = ms;
     return CVS_OK;

@@ -449,11 +449,51 @@ __global__ void __launch_bounds__(256) k_ffma(const __grid_constant__ FfmaConsts
     if (s == 123.456f) sink[0] = s;  // keeps the loop alive; never true in practice
 }
 
+// Packed fp32x2 probes (sm_100 FFMA2): FORM 3 = FFMA2 only, 4 = FFMA2 interleaved 1:1 with independent integer ALU ops,
+// 5 = scalar FFMA interleaved 1:1 with the same ALU ops.  They answer: does x2 raise FMA throughput (no: same lanes) and
+// does it free issue slots for non-FMA work (yes if FORM 4 keeps FORM 3's FMA rate while FORM 5 halves FORM 0's).
+template <int FORM>
+__global__ void __launch_bounds__(256) k_ffma2(const __grid_constant__ FfmaConsts k, int iters, float* sink, float seed)
+{
+    float2 acc[16], v[8], r[16];
+    unsigned z[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        acc[i] = make_float2(seed + threadIdx.x * 1e-6f + i, seed - i);
+        r[i] = make_float2(k.c[i] + seed, k.c[15 - i] - seed);
+        z[i] = threadIdx.x * 2654435761u + i;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = make_float2(seed + 1e-3f * (threadIdx.x + i), seed - 1e-3f * i);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                if (FORM == 5) {
+                    acc[i].x = fmaf(v[(i + u) & 7].x, r[(i + 5 * u) & 15].x, acc[i].x);
+                } else {
+                    acc[i] = __ffma2_rn(v[(i + u) & 7], r[(i + 5 * u) & 15], acc[i]);
+                }
+                if (FORM >= 4) z[i] = (z[i] ^ (z[(i + 3) & 15] >> 3)) + 0x9e3779b9u * (unsigned)(u + 1);
+            }
+        }
+    }
+    float s = 0.f;
+    unsigned zz = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += acc[i].x + acc[i].y, zz ^= z[i];
+    if (s == 123.456f || zz == 0x12345u) sink[0] = s + zz;
+}
+
 cudaError_t launch_ffma_bench(int form, int iters, int blocks, int threads, float* sink, cudaStream_t stream)
 {
     FfmaConsts k;
     for (int i = 0; i < 16; ++i) k.c[i] = (i & 1 ? -1.f : 1.f) * (0.25f + 0.03125f * i);
-    if (form == 0) k_ffma<0><<<blocks, threads, 0, stream>>>(k, iters, sink, 0.f);
+    if (form == 3) k_ffma2<3><<<blocks, threads, 0, stream>>>(k, iters, sink, 0.f);
+    else if (form == 4) k_ffma2<4><<<blocks, threads, 0, stream>>>(k, iters, sink, 0.f);
+    else if (form == 5) k_ffma2<5><<<blocks, threads, 0, stream>>>(k, iters, sink, 0.f);
+    else if (form == 0) k_ffma<0><<<blocks, threads, 0, stream>>>(k, iters, sink, 0.f);
     else if (form == 1) k_ffma<1><<<blocks, threads, 0, stream>>>(k, iters, sink, 0.f);
     else k_ffma<2><<<blocks, threads, 0, stream>>>(k, iters, sink, 0.f);
     g_launches.fetch_add(1);

@@ -206,7 +206,8 @@ CVS_API int cvs_g2_run_batch_host_multi(int n_devices, const int* devices, int w
 
 /* ---- measurement helpers (used by bench.py; not part of the reference surface) ---- */
 /* Saturating FFMA loop: returns achieved fp32 instructions/s (1 FFMA = 1 instr = 2 flop).
- * form: 0 = immediate-operand FFMA, 1 = register-operand, 2 = constant-bank operand. */
+ * form: 0 = immediate-operand FFMA, 1 = register-operand, 2 = constant-bank operand; 3 = packed FFMA2 (counted as 2 per
+ * instruction), 4 = FFMA2 interleaved 1:1 with integer ALU work, 5 = scalar FFMA interleaved 1:1 with the same ALU work. */
 CVS_API int cvs_bench_ffma(int device, int form, int iters, double* instr_per_s, float* elapsed_ms);
 /* Last kernel launch configuration of a handle, for reporting (grid, block, dynamic smem bytes, kernel name). */
 CVS_API int cvs_g2_last_launch(const cvs_g2* h, int* grid_xyz, int* block, int* smem, char* name, int name_len);
