@@ -640,6 +640,85 @@ extern "C" int cvs_g2_run_batch_host(cvs_g2* h, const float* in, int n, int rows
     return CVS_OK;
 }
 
+extern "C" int cvs_to_u8_dev(int device, const float* src, int n, int rows, int cols, size_t pitch, size_t frame_stride, float gain, uint8_t* dst,
+                             size_t dst_pitch, size_t dst_frame_stride, void* stream)
+{
+    if (!src || !dst || n <= 0 || rows <= 0 || cols <= 0) return fail(CVS_ERR_INVALID_ARG, "bad argument");
+    if (pitch < (size_t)cols * 4 || dst_pitch < (size_t)cols) return fail(CVS_ERR_INVALID_ARG, "pitch too small");
+    CU_TRY(cudaSetDevice(device));
+    unsigned* mm = nullptr;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (!(gain > 0.f)) CU_TRY(cudaMallocAsync(reinterpret_cast<void**>(&mm), sizeof(unsigned) * 2 * n, s));
+    cudaError_t e = launch_to_u8(src, pitch, frame_stride, n, rows, cols, gain, mm, dst, dst_pitch, dst_frame_stride, s);
+    if (mm) cudaFreeAsync(mm, s);
+    CU_TRY(e);
+    return CVS_OK;
+}
+
+extern "C" int cvs_g2_lines_u8_host(cvs_g2* h, const uint8_t* gray, int n, int rows, int cols, size_t step, size_t frame_stride, float gain,
+                                    uint8_t* edges, uint8_t* lines_dark, uint8_t* lines_bright, size_t out_step, size_t out_frame_stride)
+{
+    Filter* f = reinterpret_cast<Filter*>(h);
+    if (!f || f->family != 2 || !gray) return fail(CVS_ERR_INVALID_ARG, "null argument");
+    if (n <= 0 || rows <= 0 || cols <= 0 || n > 65535) return fail(CVS_ERR_INVALID_ARG, "n/rows/cols out of range");
+    if (step < (size_t)cols || out_step < (size_t)cols) return fail(CVS_ERR_INVALID_ARG, "step < cols");
+    uint8_t* outs8[3] = {edges, lines_dark, lines_bright};
+    const int planes[3] = {CVS_EDGES, CVS_DARK, CVS_BRIGHT};
+    unsigned mask = 0;
+    for (int i = 0; i < 3; ++i)
+        if (outs8[i]) mask |= CVS_BIT(planes[i]);
+    if (!mask) return fail(CVS_ERR_INVALID_ARG, "no output requested");
+    CU_TRY(cudaSetDevice(f->device));
+    const size_t pin = align_up((size_t)cols, 128), pf = align_up((size_t)cols * 4, 128), p8 = align_up((size_t)cols, 128);
+    const size_t in_bytes = pin * rows * n, f_bytes = pf * rows * n, o_bytes = p8 * rows * n;
+    // work buffer: [u8 in][3 float maps][3 u8 maps][min/max]
+    CU_TRY(f->work.reserve(in_bytes + 3 * f_bytes + 3 * o_bytes + sizeof(unsigned) * 2 * n + 256));
+    char* w = static_cast<char*>(f->work.p);
+    uint8_t* din = reinterpret_cast<uint8_t*>(w);
+    float* dmap[3];
+    uint8_t* dout[3];
+    for (int i = 0; i < 3; ++i) dmap[i] = reinterpret_cast<float*>(w + in_bytes + i * f_bytes);
+    for (int i = 0; i < 3; ++i) dout[i] = reinterpret_cast<uint8_t*>(w + in_bytes + 3 * f_bytes + i * o_bytes);
+    unsigned* mm = reinterpret_cast<unsigned*>(w + align_up(in_bytes + 3 * f_bytes + 3 * o_bytes, 16));
+    cudaStream_t s = f->stream;
+    cudaMemcpy3DParms cp{};
+    cp.srcPtr = make_cudaPitchedPtr(const_cast<uint8_t*>(gray), step, cols, frame_stride / step);
+    cp.dstPtr = make_cudaPitchedPtr(din, pin, cols, rows);
+    cp.extent = make_cudaExtent(cols, rows, n);
+    cp.kind = cudaMemcpyHostToDevice;
+    if (n == 1 || frame_stride % step == 0) {
+        CU_TRY(cudaMemcpy3DAsync(&cp, s));
+    } else {
+        for (int k = 0; k < n; ++k)
+            CU_TRY(cudaMemcpy2DAsync(din + (size_t)k * pin * rows, pin, gray + (size_t)k * frame_stride, step, cols, rows, cudaMemcpyHostToDevice, s));
+    }
+    BatchGeom g = whole_frame_geom(din, true, n, rows, cols, pin, pin * rows, pf, pf * rows);
+    float* outs[CVS_G2_NPLANES] = {nullptr};
+    for (int i = 0; i < 3; ++i) outs[planes[i]] = dmap[i];
+    SteerSpec st{};
+    st.source = CVS_STEER_DOMINANT;
+    int rc = run_fused(f, g, mask, st, outs, s);
+    if (rc) return rc;
+    for (int i = 0; i < 3; ++i) {
+        if (!outs8[i]) continue;
+        CU_TRY(launch_to_u8(dmap[i], pf, pf * rows, n, rows, cols, gain, mm, dout[i], p8, p8 * rows, s));
+        cudaMemcpy3DParms cq{};
+        cq.srcPtr = make_cudaPitchedPtr(dout[i], p8, cols, rows);
+        cq.dstPtr = make_cudaPitchedPtr(outs8[i], out_step, cols, out_frame_stride / out_step);
+        cq.extent = make_cudaExtent(cols, rows, n);
+        cq.kind = cudaMemcpyDeviceToHost;
+        if (n == 1 || out_frame_stride % out_step == 0) {
+            CU_TRY(cudaMemcpy3DAsync(&cq, s));
+        } else {
+            for (int k = 0; k < n; ++k)
+                CU_TRY(cudaMemcpy2DAsync(outs8[i] + (size_t)k * out_frame_stride, out_step, dout[i] + (size_t)k * p8 * rows, p8, cols, rows,
+                                         cudaMemcpyDeviceToHost, s));
+        }
+    }
+    CU_TRY(cudaStreamSynchronize(s));
+    return CVS_OK;
+}
+
 extern "C" int cvs_g2_run_batch_host_multi(int n_devices, const int* devices, int width, float spacing, const float* in, int n, int rows,
                                            int cols, size_t in_step, size_t in_frame_stride, unsigned mask, float* const* outs,
                                            size_t out_step, size_t out_frame_stride)

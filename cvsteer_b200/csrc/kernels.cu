@@ -413,6 +413,85 @@ cudaError_t launch_pyr_down(const BatchGeom& g, float* out, cudaStream_t stream)
 }
 
 // ------------------------------------------------------------------------------------------------
+// 8-bit output maps: the callers' post-processing (reference example/steer.cpp:92-104, test/test.cpp:93-95).
+//   gain > 0 : Mat::convertTo(CV_8UC1, gain)                       dst = saturate_u8(rint(src * gain))
+//   gain <= 0: cv::normalize(src, dst, 0, 255, NORM_MINMAX, CV_8UC1) dst = saturate_u8(rint(src * scale + shift)),
+//              scale = 255 / (max - min) (0 if max - min <= DBL_EPSILON), shift = -min * scale, per frame
+// Two small HBM-bound kernels per plane; min/max stay on the device (no host round trip between them).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned ordered_u32(float f)
+{
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // monotone map float -> unsigned (NaNs are skipped by the caller)
+}
+__device__ __forceinline__ float unordered_f32(unsigned u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+
+__global__ void k_minmax_init(unsigned* mm, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) mm[2 * i] = 0xffffffffu, mm[2 * i + 1] = 0u;
+}
+
+__global__ void __launch_bounds__(256) k_minmax(const float* src, long long pitch, long long frame_stride, int rows, int cols, unsigned* mm)
+{
+    const int frame = blockIdx.y;
+    const char* base = reinterpret_cast<const char*>(src) + (long long)frame * frame_stride;
+    unsigned lo = 0xffffffffu, hi = 0u;
+    for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+        const float* row = reinterpret_cast<const float*>(base + (long long)r * pitch);
+        for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+            const float v = row[c];
+            if (v == v) {
+                const unsigned o = ordered_u32(v);
+                lo = min(lo, o), hi = max(hi, o);
+            }
+        }
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&mm[2 * frame], lo);
+        atomicMax(&mm[2 * frame + 1], hi);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_to_u8(const float* src, long long pitch, long long frame_stride, int rows, int cols, float gain,
+                                               const unsigned* mm, unsigned char* dst, long long dpitch, long long dframe_stride)
+{
+    const int frame = blockIdx.z, r = blockIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    float scale = gain, shift = 0.f;
+    if (!(gain > 0.f)) {
+        const double smin = unordered_f32(mm[2 * frame]), smax = unordered_f32(mm[2 * frame + 1]);
+        const double sc = 255.0 * ((smax - smin > 2.220446049250313e-16) ? 1.0 / (smax - smin) : 0.0);
+        scale = (float)sc;
+        shift = (float)(0.0 - smin * sc);
+    }
+    const float v = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(src) + (long long)frame * frame_stride + (long long)r * pitch + 4ll * c);
+    // saturate_cast<uchar>(cvRound(v*scale + shift)): round-half-even then clamp
+    const int q = __float2int_rn(fmaf(v, scale, shift));
+    dst[(long long)frame * dframe_stride + (long long)r * dpitch + c] = (unsigned char)min(max(q, 0), 255);
+}
+
+cudaError_t launch_to_u8(const float* src, size_t pitch, size_t frame_stride, int n, int rows, int cols, float gain, unsigned* minmax_scratch,
+                         unsigned char* dst, size_t dpitch, size_t dframe_stride, cudaStream_t stream)
+{
+    if (n <= 0 || rows <= 0 || cols <= 0 || n > 65535 || rows > 65535) return cudaErrorInvalidValue;
+    if (!(gain > 0.f)) {
+        if (!minmax_scratch) return cudaErrorInvalidValue;
+        k_minmax_init<<<(n + 255) / 256, 256, 0, stream>>>(minmax_scratch, n);
+        const int bx = rows < 296 ? rows : 296;  // 2 CTAs per SM worth of row-striding blocks per frame
+        k_minmax<<<dim3(bx, n), 256, 0, stream>>>(src, (long long)pitch, (long long)frame_stride, rows, cols, minmax_scratch);
+        g_launches.fetch_add(2);
+    }
+    k_to_u8<<<dim3((cols + 255) / 256, rows, n), 256, 0, stream>>>(src, (long long)pitch, (long long)frame_stride, rows, cols, gain, minmax_scratch,
+                                                                  dst, (long long)dpitch, (long long)dframe_stride);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // FP32 roofline denominator: a saturating FFMA loop in the three operand forms the stencil can use.
 // ------------------------------------------------------------------------------------------------
 struct FfmaConsts {

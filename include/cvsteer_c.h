@@ -195,6 +195,17 @@ CVS_API int cvs_g2_run_batch_host(cvs_g2* h, const float* in, int n, int rows, i
                                   size_t in_frame_stride, unsigned mask, float* const* outs,
                                   size_t out_step, size_t out_frame_stride);
 
+/* ---- the callers' 8-bit post-processing (reference example/steer.cpp:92-104, test/test.cpp:93-95), on the device ----
+ * gain > 0: Mat::convertTo(CV_8UC1, gain); gain <= 0: cv::normalize(src, dst, 0, 255, NORM_MINMAX, CV_8UC1), per frame. */
+CVS_API int cvs_to_u8_dev(int device, const float* src, int n, int rows, int cols, size_t pitch, size_t frame_stride, float gain,
+                          uint8_t* dst, size_t dst_pitch, size_t dst_frame_stride, void* stream);
+/* The whole per-file body of cvsteer-run (example/steer.cpp:73-104) for a batch of 8-bit gray frames in host memory:
+ * SteerableFiltersG2(gray) -> steer(theta_d, ...) -> findEdges / findDarkLines / findBrightLines(magnitude, phase) ->
+ * 8-bit maps.  One fused launch + the conversion kernels per batch; any of the three outputs may be NULL. */
+CVS_API int cvs_g2_lines_u8_host(cvs_g2* h, const uint8_t* gray, int n, int rows, int cols, size_t step, size_t frame_stride,
+                                 float gain, uint8_t* edges, uint8_t* lines_dark, uint8_t* lines_bright, size_t out_step,
+                                 size_t out_frame_stride);
+
 /* Same call sharded by frame over `n_devices` GPUs of this process (devices[i], or 0..n-1 when devices == NULL):
  * contiguous blocks of ceil(n/n_devices) frames, one host thread + one handle + its own streams per GPU, NO collective
  * (frames are independent units, as the reference's cv::parallel_for_ over files is: example/steer.cpp:169).
