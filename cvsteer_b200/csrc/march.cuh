@@ -25,6 +25,17 @@
 
 #include "device_math.cuh"
 
+// 1: static-mask kernels of families without a shared row pass replicate the whole row body per window slot (no slot
+// dispatch in the loop).  Measured on B200: M1 155 -> 180 Gpix/s, M2 122 -> 132 Gpix/s versus the switch-based loop.
+#ifndef CVS_MARCH_UNROLL_EPILOGUE
+#define CVS_MARCH_UNROLL_EPILOGUE 1
+#endif
+// 1: the slot dispatch of the rolled loop is a balanced compare tree instead of a switch (which nvcc lowers to a
+// constant-memory jump table: LDC + BRX on the critical path of every row).
+#ifndef CVS_MARCH_TREE_DISPATCH
+#define CVS_MARCH_TREE_DISPATCH 1
+#endif
+
 namespace cvs {
 
 // ------------------------------------------------------------------------------------------------
@@ -100,6 +111,19 @@ template <int NSETS, int R>
 struct TapTable {
     float t[NSETS][R + 1];
 };
+
+// Balanced compare tree over [LO, HI): calls f(integral_constant<int, slot>) for the run-time `slot`.
+template <int LO, int HI, class F>
+__device__ __forceinline__ void dispatch_tree(int slot, F&& f)
+{
+    if constexpr (HI - LO == 1) {
+        f(std::integral_constant<int, LO>{});
+    } else {
+        constexpr int MID = (LO + HI) / 2;
+        if (slot < MID) dispatch_tree<LO, MID>(slot, f);
+        else dispatch_tree<MID, HI>(slot, f);
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
 // Output cursor: where this thread's pixel of the current row lives in every output plane.
@@ -343,6 +367,26 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
     const long long band_off = (long long)frame * a.out_frame_stride + (long long)(yb - a.out_row_origin) * a.out_pitch;
     // per-plane base registers only pay off while there are few planes (2 registers each); wide masks share one offset
     OutCursor<(__builtin_popcount(MASK) <= 8 ? MASK : 0u), Fam::NPLANES> cur(a, band_off, x);
+    if constexpr (CVS_MARCH_UNROLL_EPILOGUE && MASK != 0 && !Fam::SHARED_ROW_PASS) {
+        // Variant for short epilogues: the whole row body (row pass, column pass, epilogue) is replicated per slot, so the
+        // loop needs no slot dispatch at all.  Only worth it while K x (body) still fits the instruction cache.
+        auto body = [&](int rt, auto slot_c) {
+            row_pass(rt);
+            col_pass(rt >= 2 * R, slot_c);
+            if (rt >= 2 * R) {
+                Fam::template epilogue<MASK>(b, a, cur, 0.f);
+                cur.next_row();
+            }
+        };
+        const int total = nrows + 2 * R;
+#pragma unroll 1
+        for (int rt0 = 0; rt0 < total; rt0 += K) {
+            [&]<int... I>(std::integer_sequence<int, I...>) {
+                ((rt0 + I < total ? body(rt0 + I, std::integral_constant<int, I>{}) : void()), ...);
+            }(std::make_integer_sequence<int, K>{});
+        }
+        return;
+    }
     int slot = 0;
 #pragma unroll 1
     for (int rt = 0; rt < nrows + 2 * R; ++rt) {
@@ -351,6 +395,12 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
         float theta_px = 0.f;
         if (Fam::template reads_theta_map<MASK>(a) && rt >= 2 * R) theta_px = cur.theta(a);
         if constexpr (Fam::SHARED_ROW_PASS) row_pass(rt);
+#if CVS_MARCH_TREE_DISPATCH
+        dispatch_tree<0, K>(slot, [&](auto slot_c) {
+            if constexpr (!Fam::SHARED_ROW_PASS) row_pass(rt);
+            col_pass(rt >= 2 * R, slot_c);
+        });
+#else
         switch (slot) {
 #define CVS_CASE(I)                                                        \
     case I:                                                                \
@@ -364,6 +414,7 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
 #undef CVS_CASE
             default: break;
         }
+#endif
         slot = (slot + 1 == K) ? 0 : slot + 1;
         if (rt >= 2 * R) {
             Fam::template epilogue<MASK>(b, a, cur, theta_px);
