@@ -39,6 +39,29 @@ __device__ __forceinline__ float fast_sqrt(float x)
     return r;
 }
 
+// sin/cos for a steering angle.  |x| <= pi/2 (every dominant-orientation angle) takes two short minimax polynomials in
+// x^2 (abs error 1.4e-7 in fp32, the same order as cv::polarToCart's own error); anything else takes libdevice's
+// accurate sincosf.  The branch is warp-uniform in practice (angle maps are either all theta_d or all arbitrary).
+__device__ __forceinline__ void sincos_steer(float x, float* s, float* c)
+{
+    if (fabsf(x) <= 1.5709f) {
+        const float t = x * x;
+        float ps = fmaf(t, 2.605136842248612e-06f, -0.00019809033256024122f);
+        ps = fmaf(ps, t, 0.008333050645887852f);
+        ps = fmaf(ps, t, -0.16666658222675323f);
+        ps = fmaf(ps, t, 1.0f);
+        float pc = fmaf(t, -2.6050781798403477e-07f, 2.4760118321864866e-05f);
+        pc = fmaf(pc, t, -0.0013888360699638724f);
+        pc = fmaf(pc, t, 0.04166663438081741f);
+        pc = fmaf(pc, t, -0.5f);
+        pc = fmaf(pc, t, 1.0f);
+        *s = ps * x;
+        *c = pc;
+    } else {
+        sincosf(x, s, c);
+    }
+}
+
 // cv::cartToPolar's angle (hal::fastAtan32f, in radians, range [0, 2pi)): 7th-order odd polynomial in
 // min/max, evaluated with FMAs as OpenCV's SIMD path does.  With FAST = false (IEEE division) this is
 // bit-identical to cv2 4.13.0 on 2M random points; FAST = true replaces the division by MUFU.RCP (<= 2 ulp on

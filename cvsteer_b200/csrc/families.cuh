@@ -100,7 +100,7 @@ struct G2Fam {
                 ct = a.cos_t;
                 st = a.sin_t;
             } else {
-                sincosf(theta_px, &st, &ct);
+                dev::sincos_steer(theta_px, &st, &ct);
             }
             // cos 2t = c^2 - s^2, sin 2t = 2cs  (reference: polarToCart(2*theta), G2.cpp:175)
             if (m & CVS_BIT(CVS_E)) put(CVS_E, fmaf(o.c2, fmaf(ct, ct, -st * st), fmaf(o.c3, 2.f * ct * st, o.c1)));
@@ -175,7 +175,7 @@ struct G4Fam {
             ct = a.cos_t;
             st = a.sin_t;
         } else {
-            sincosf(theta_px, &st, &ct);
+            dev::sincos_steer(theta_px, &st, &ct);
         }
         float g4, h4;
         dev::steer_g4(ct, st, &b[0], &b[5], g4, h4);

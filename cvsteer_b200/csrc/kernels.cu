@@ -163,7 +163,7 @@ __global__ void k_g2_steer_planes(const __grid_constant__ PlaneSteerArgs a)
         ct = a.cos_t, st = a.sin_t, c2t = a.cos2t, s2t = a.sin2t;
     } else {
         const float th = at(a.theta, a.theta_pitch, y, x);
-        sincosf(th, &st, &ct);
+        dev::sincos_steer(th, &st, &ct);
         c2t = fmaf(ct, ct, -st * st);
         s2t = 2.f * ct * st;
     }
@@ -196,7 +196,7 @@ __global__ void k_g4_steer_planes(const __grid_constant__ PlaneSteerArgs a)
     if (a.source == CVS_STEER_SCALAR) {
         ct = a.cos_t, st = a.sin_t;
     } else {
-        sincosf(at(a.theta, a.theta_pitch, y, x), &st, &ct);
+        dev::sincos_steer(at(a.theta, a.theta_pitch, y, x), &st, &ct);
     }
     float g4, h4;
     dev::steer_g4(ct, st, &b[0], &b[5], g4, h4);
