@@ -266,3 +266,41 @@ def test_multi_device_host_api():
                                                           capi.G2_MASK_ORIENT, arr, 130 * 4, 90 * 130 * 4))
         for p in planes:
             assert np.array_equal(outs[p], want[capi.G2_PLANE_NAMES[p]].cpu().numpy()), (nd, p)
+
+
+def test_generic_width_band_equals_whole():
+    H, W = 150, 170
+    img = synth(3960, H, W)
+    g = G2Batch(width=6, spacing=0.45)
+    whole = g.run(torch.from_numpy(img[None]).cuda(), capi.G2_MASK_FULL)
+    assert g.last_launch()["kernel"].startswith("generic")
+    for (r0, r1) in ((0, 70), (70, 150)):
+        lo, hi = max(0, r0 - 6), min(H, r1 + 6)
+        part = g.run(torch.from_numpy(img[None, lo:hi].copy()).cuda(), capi.G2_MASK_FULL, band=Band(full_rows=H, y_origin=lo, row_begin=r0, row_end=r1))
+        for k in whole:
+            assert torch.equal(part[k][0], whole[k][0, r0:r1]), (k, r0)
+
+
+def test_huge_single_image_64bit_indexing():
+    """One 32768 x 20000 frame (2.6 GB in, 7.9 GB out): plane offsets exceed 2^32 bytes; crops are checked against the
+    oracle run on the same crops (far from borders the supports coincide)."""
+    H, W = 32768, 20000
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(5)
+    x = torch.rand((1, H, W), device="cuda", generator=gen) * 255
+    g = G2Batch()
+    r = g.run(x, capi.G2_MASK_ORIENT)
+    for (y0, x0) in ((100, 100), (32768 - 300, 20000 - 400), (30000, 123), (16384, 9000)):
+        crop = x[0, y0:y0 + 160, x0:x0 + 200].cpu().numpy()
+        o = ref.SteerableFiltersG2(crop)
+        rng = basis_range([getattr(o, k) for k in STATE])
+        got = r["strength"][0, y0 + 8:y0 + 152, x0 + 8:x0 + 192].cpu().numpy()
+        assert_close_range(got, o.strength[8:-8, 8:-8], rng * rng, f"strength crop {(y0, x0)}")
+        th = r["theta"][0, y0 + 8:y0 + 152, x0 + 8:x0 + 192].cpu().numpy()
+        assert_angle_close(th, o.theta[8:-8, 8:-8], o.strength[8:-8, 8:-8], np.pi, f"theta crop {(y0, x0)}")
+    # bottom border rows use reflect-101 of the true last rows
+    o = ref.SteerableFiltersG2(x[0, H - 120:, 5000:5200].cpu().numpy())
+    rng = basis_range([getattr(o, k) for k in STATE])
+    assert_close_range(r["strength"][0, H - 100:, 5008:5192].cpu().numpy(), o.strength[20:, 8:-8], rng * rng, "bottom border")
+    del r, x
+    torch.cuda.empty_cache()

@@ -83,3 +83,24 @@ def test_fused_batch_steer_phase():
     assert_close_range(r2["g4"][0].cpu().numpy(), w[0], 1000.0, "g4 scalar fused")
     with pytest.raises(capi.CvsError):
         g.run(torch.from_numpy(fr).cuda(), capi.G4_MASK_STEER)  # no dominant orientation in G4 (reference G4.h:40-41)
+
+
+def test_g4_band_equals_whole_and_u8_input():
+    from cvsteer_b200.batch import Band
+    H, W = 260, 300
+    img = synth(4300, H, W)
+    g = G4Batch()
+    th = np.random.default_rng(2).uniform(-1.5, 1.5, (1, H, W)).astype(np.float32)
+    mask = capi.G4_MASK_STEER
+    whole = g.run(torch.from_numpy(img[None]).cuda(), mask, steer=capi.STEER_MAP, theta_map=torch.from_numpy(th).cuda())
+    for (r0, r1) in ((0, 64), (64, 200), (200, 260)):
+        lo, hi = max(0, r0 - 6), min(H, r1 + 6)
+        part = g.run(torch.from_numpy(img[None, lo:hi].copy()).cuda(), mask, steer=capi.STEER_MAP,
+                     theta_map=torch.from_numpy(th[:, r0:r1].copy()).cuda(), band=Band(full_rows=H, y_origin=lo, row_begin=r0, row_end=r1))
+        for k in whole:
+            assert torch.equal(part[k][0], whole[k][0, r0:r1]), (k, r0)
+    img8 = np.random.default_rng(3).integers(0, 256, (1, 90, 140), dtype=np.uint8)
+    a = g.run(torch.from_numpy(img8).cuda(), capi.G4_MASK_BASIS)
+    b = g.run(torch.from_numpy(img8.astype(np.float32)).cuda(), capi.G4_MASK_BASIS)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
