@@ -367,29 +367,38 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
     const long long band_off = (long long)frame * a.out_frame_stride + (long long)(yb - a.out_row_origin) * a.out_pitch;
     // per-plane base registers only pay off while there are few planes (2 registers each); wide masks share one offset
     OutCursor<(__builtin_popcount(MASK) <= 8 ? MASK : 0u), Fam::NPLANES> cur(a, band_off, x);
+    int rt_done = 0;  // tile rows already consumed by the unrolled path below (always a multiple of K)
     if constexpr (CVS_MARCH_UNROLL_EPILOGUE && MASK != 0 && !Fam::SHARED_ROW_PASS) {
         // Variant for short epilogues: the whole row body (row pass, column pass, epilogue) is replicated per slot, so the
         // loop needs no slot dispatch at all.  Only worth it while K x (body) still fits the instruction cache.
-        auto body = [&](int rt, auto slot_c) {
-            row_pass(rt);
-            col_pass(rt >= 2 * R, slot_c);
-            if (rt >= 2 * R) {
-                Fam::template epilogue<MASK>(b, a, cur, 0.f);
-                cur.next_row();
-            }
-        };
+        // Groups of K rows run WITHOUT per-row bounds checks, i.e. as one basic block that the scheduler can overlap
+        // across rows (next row's shared-memory loads under the previous row's epilogue).  BH + 2R is a multiple of K for
+        // the G2 family (64 + 8 = 8 x 9), so a full band is exactly group 0 (2R window-filling rows + the first output row)
+        // plus whole groups; only the last band of an image leaves a remainder for the rolled loop below.
+        static_assert(2 * R == K - 1, "group 0 = 2R pre-roll rows + 1 output row");
         const int total = nrows + 2 * R;
-#pragma unroll 1
-        for (int rt0 = 0; rt0 < total; rt0 += K) {
+        if (total >= K) {
             [&]<int... I>(std::integer_sequence<int, I...>) {
-                ((rt0 + I < total ? body(rt0 + I, std::integral_constant<int, I>{}) : void()), ...);
-            }(std::make_integer_sequence<int, K>{});
-        }
-        return;
-    }
-    int slot = 0;
+                ((row_pass(I), col_pass(false, std::integral_constant<int, I>{})), ...);
+            }(std::make_integer_sequence<int, 2 * R>{});
+            row_pass(2 * R);
+            col_pass(true, std::integral_constant<int, 2 * R>{});
+            Fam::template epilogue<MASK>(b, a, cur, 0.f);
+            cur.next_row();
+            rt_done = K;
 #pragma unroll 1
-    for (int rt = 0; rt < nrows + 2 * R; ++rt) {
+            for (; rt_done + K <= total; rt_done += K) {
+                [&]<int... I>(std::integer_sequence<int, I...>) {
+                    ((row_pass(rt_done + I), col_pass(true, std::integral_constant<int, I>{}), Fam::template epilogue<MASK>(b, a, cur, 0.f),
+                      cur.next_row()),
+                     ...);
+                }(std::make_integer_sequence<int, K>{});
+            }
+        }
+    }
+    int slot = 0;  // rt_done is a multiple of K, so the window slot of tile row rt_done is 0 again
+#pragma unroll 1
+    for (int rt = rt_done; rt < nrows + 2 * R; ++rt) {
         // steering-angle map: issue the load for this output row before ~all of the row's arithmetic, so that its DRAM
         // latency is covered by the row/column passes instead of stalling the epilogue
         float theta_px = 0.f;
