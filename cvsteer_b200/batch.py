@@ -79,8 +79,10 @@ class _FusedBatch:
 
     def run(self, frames: torch.Tensor, mask: int, steer: int = capi.STEER_DOMINANT, theta: float = 0.0,
             theta_map: Optional[torch.Tensor] = None, outs: Optional[Dict[int, torch.Tensor]] = None,
-            band: Optional[Band] = None, stream=None) -> Dict[str, torch.Tensor]:
-        """One fused launch over the whole batch.  Returns {plane name: tensor [n, out_rows, cols]}."""
+            band: Optional[Band] = None, stream=None, next_level: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """One fused launch over the whole batch.  Returns {plane name: tensor [n, out_rows, cols]}.
+        next_level: optional contiguous float32 [n, (rows+1)//2, (cols+1)//2]; the same launch fills it with
+        cv::pyrDown(frames) from the tile it stages anyway (whole frames only)."""
         x = _as_batch(frames)
         n, rows, cols = x.shape
         out_rows = rows if band is None else band.row_end - band.row_begin
@@ -100,6 +102,12 @@ class _FusedBatch:
                 raise capi.CvsError(capi.ERR_SIZE_MISMATCH, "theta_map must be contiguous float32 [n, out_rows, cols]")
             tm = C.c_void_p(theta_map.data_ptr())
         b = _batch_struct(x, cols * 4, out_rows * cols * 4, band)
+        if next_level is not None:
+            want = (n, (rows + 1) // 2, (cols + 1) // 2)
+            if tuple(next_level.shape) != want or next_level.dtype != torch.float32 or not next_level.is_contiguous():
+                raise capi.CvsError(capi.ERR_SIZE_MISMATCH, f"next_level must be contiguous float32 {want}")
+            b.next_level = next_level.data_ptr()
+            b.next_pitch, b.next_frame_stride = want[2] * 4, want[1] * want[2] * 4
         fn = getattr(self._lib, f"cvs_{self._prefix}_run_batch_dev")
         capi.check(fn(self._h, C.byref(b), mask, steer, theta, tm, arr, _stream_ptr(stream)))
         return {self._names[p]: outs[p] for p in planes}
@@ -108,10 +116,15 @@ class _FusedBatch:
         """Every pyramid level stays resident on the device: level l+1 = pyr_down(level l), then one fused
         launch per level (config 3 of BASELINE.json)."""
         res, cur = [], _as_batch(frames)
+        fuse = kw.pop("fuse_pyramid", True)
         for l in range(levels):
-            res.append(self.run(cur, mask, **kw))
+            nxt = None
+            if l + 1 < levels and fuse:
+                n, r, c = cur.shape
+                nxt = torch.empty((n, (r + 1) // 2, (c + 1) // 2), dtype=torch.float32, device=cur.device)
+            res.append(self.run(cur, mask, next_level=nxt, **kw))
             if l + 1 < levels:
-                cur = pyr_down(cur, stream=kw.get("stream"))
+                cur = nxt if fuse else pyr_down(cur, stream=kw.get("stream"))
         return res
 
     def last_launch(self):

@@ -43,7 +43,8 @@ class Batch(C.Structure):
     _fields_ = [("in_", C.c_void_p), ("in_is_u8", C.c_int), ("n", C.c_int), ("rows", C.c_int), ("cols", C.c_int),
                 ("in_pitch", C.c_size_t), ("in_frame_stride", C.c_size_t), ("out_pitch", C.c_size_t),
                 ("out_frame_stride", C.c_size_t), ("full_rows", C.c_int), ("y_origin", C.c_int),
-                ("out_row_begin", C.c_int), ("out_row_end", C.c_int), ("out_row_origin", C.c_int)]
+                ("out_row_begin", C.c_int), ("out_row_end", C.c_int), ("out_row_origin", C.c_int),
+                ("next_level", C.c_void_p), ("next_pitch", C.c_size_t), ("next_frame_stride", C.c_size_t)]
 
 
 class CvsError(RuntimeError):

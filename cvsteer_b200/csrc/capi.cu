@@ -188,6 +188,13 @@ int geom_from_batch(const cvs_batch* b, BatchGeom* g)
     if (b->out_pitch < (size_t)b->cols * 4 / 2) return fail(CVS_ERR_INVALID_ARG, "out_pitch too small");
     *g = whole_frame_geom(b->in, b->in_is_u8 != 0, b->n, b->rows, b->cols, b->in_pitch, b->in_frame_stride, b->out_pitch,
                           b->out_frame_stride);
+    if (b->next_level) {
+        if (b->full_rows > 0) return fail(CVS_ERR_UNSUPPORTED, "next_level fusion is for whole frames; bands use cvs_pyr_down_dev");
+        if (b->next_pitch < (size_t)((b->cols + 1) / 2) * 4) return fail(CVS_ERR_INVALID_ARG, "next_pitch too small");
+        g->next_level = b->next_level;
+        g->next_pitch = b->next_pitch;
+        g->next_frame_stride = b->next_frame_stride;
+    }
     if (b->full_rows > 0) {
         g->full_rows = b->full_rows;
         g->y_origin = b->y_origin;

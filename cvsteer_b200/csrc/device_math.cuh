@@ -39,6 +39,13 @@ __device__ __forceinline__ float fast_sqrt(float x)
     return r;
 }
 
+// cv::pyrDown's 5-tap [1 4 6 4 1] in OpenCV's float order (6*c + 4*(l1+r1) + l2 + r2), spelled with explicit FMAs so
+// that every kernel that builds a pyramid level (stand-alone or fused into the basis kernel) rounds identically.
+__device__ __forceinline__ float pyr_tap5(float v0, float v1, float v2, float v3, float v4)
+{
+    return fmaf(v1 + v3, 4.f, v2 * 6.f) + v0 + v4;
+}
+
 // sin/cos for a steering angle.  |x| <= pi/2 (every dominant-orientation angle) takes two short minimax polynomials in
 // x^2 (abs error 1.4e-7 in fp32, the same order as cv::polarToCart's own error); anything else takes libdevice's
 // accurate sincosf.  The branch is warp-uniform in practice (angle maps are either all theta_d or all arbitrary).

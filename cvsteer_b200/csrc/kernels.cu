@@ -121,8 +121,15 @@ cudaError_t launch_basis_fused(int family, const FamilyTaps& taps, const BatchGe
     const int out_rows = g.out_row_end - g.out_row_begin;
     if (out_rows <= 0 || g.cols <= 0 || g.n <= 0) return cudaErrorInvalidValue;
     if (!uses_march_path(family, taps.width)) {
-        return family == 2 ? launch_generic<G2Fam>(taps, g, a, scratch, stream, info)
-                           : launch_generic<G4Fam>(taps, g, a, scratch, stream, info);
+        cudaError_t e = family == 2 ? launch_generic<G2Fam>(taps, g, a, scratch, stream, info)
+                                    : launch_generic<G4Fam>(taps, g, a, scratch, stream, info);
+        if (e == cudaSuccess && g.next_level) {  // no tile to emit from on this path: stand-alone pyr_down
+            BatchGeom pg = g;
+            pg.out_pitch = g.next_pitch, pg.out_frame_stride = g.next_frame_stride;
+            pg.out_row_begin = 0, pg.out_row_end = (g.full_rows + 1) / 2, pg.out_row_origin = 0;
+            e = launch_pyr_down(pg, g.next_level, stream);
+        }
+        return e;
     }
     if (g.n > 65535) return cudaErrorInvalidValue;  // callers split larger batches
     return family == 2 ? launch_march_g2(taps, g, a, st.source == CVS_STEER_DOMINANT, stream, info)
@@ -309,9 +316,9 @@ __global__ void k_pyr_down(const __grid_constant__ MarchArgs a, float* out, int 
         const int gy = dev::reflect101(2 * yo + j - 2, a.full_rows) - a.y_origin;
         const TIn* src = reinterpret_cast<const TIn*>(base + (long long)gy * a.in_pitch);
         const float v0 = (float)src[xs[0]], v1 = (float)src[xs[1]], v2 = (float)src[xs[2]], v3 = (float)src[xs[3]], v4 = (float)src[xs[4]];
-        r[j] = v2 * 6.f + (v1 + v3) * 4.f + v0 + v4;
+        r[j] = dev::pyr_tap5(v0, v1, v2, v3, v4);
     }
-    const float v = (r[2] * 6.f + (r[1] + r[3]) * 4.f + r[0] + r[4]) * (1.f / 256.f);
+    const float v = dev::pyr_tap5(r[0], r[1], r[2], r[3], r[4]) * (1.f / 256.f);
     *reinterpret_cast<float*>(reinterpret_cast<char*>(out) + (long long)frame * a.out_frame_stride +
                               (long long)(yo - a.out_row_origin) * a.out_pitch + 4ll * xo) = v;
 }
@@ -352,7 +359,7 @@ __global__ void __launch_bounds__(PD_THREADS) k_pyr_down_march(const __grid_cons
             e = src[xs4];
         }
     };
-    auto hsum = [](const float2& p, const float2& q, float e) { return q.x * 6.f + (p.y + q.y) * 4.f + p.x + e; };
+    auto hsum = [](const float2& p, const float2& q, float e) { return dev::pyr_tap5(p.x, p.y, q.x, q.y, e); };
     float h0, h1, h2, h3, h4;
     {
         float2 p0, q0, p1, q1, p2, q2;
@@ -375,8 +382,8 @@ __global__ void __launch_bounds__(PD_THREADS) k_pyr_down_march(const __grid_cons
         load_row(2 * yo + 4, p6, q6, e6);
         h3 = hsum(p3, q3, e3), h4 = hsum(p4, q4, e4);
         const float h5 = hsum(p5, q5, e5), h6 = hsum(p6, q6, e6);
-        dst[0] = (h2 * 6.f + (h1 + h3) * 4.f + h0 + h4) * (1.f / 256.f);
-        dst[opitch] = (h4 * 6.f + (h3 + h5) * 4.f + h2 + h6) * (1.f / 256.f);
+        dst[0] = dev::pyr_tap5(h0, h1, h2, h3, h4) * (1.f / 256.f);
+        dst[opitch] = dev::pyr_tap5(h2, h3, h4, h5, h6) * (1.f / 256.f);
         dst += 2 * opitch;
         h0 = h4, h1 = h5, h2 = h6;
     }
@@ -386,7 +393,7 @@ __global__ void __launch_bounds__(PD_THREADS) k_pyr_down_march(const __grid_cons
         load_row(2 * yo + 1, p3, q3, e3);
         load_row(2 * yo + 2, p4, q4, e4);
         h3 = hsum(p3, q3, e3), h4 = hsum(p4, q4, e4);
-        dst[0] = (h2 * 6.f + (h1 + h3) * 4.f + h0 + h4) * (1.f / 256.f);
+        dst[0] = dev::pyr_tap5(h0, h1, h2, h3, h4) * (1.f / 256.f);
     }
 }
 

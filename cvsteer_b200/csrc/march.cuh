@@ -102,6 +102,9 @@ struct MarchArgs {
     float cos_t, sin_t;        // scalar steering angle
     const float* theta_map;    // per-pixel angle map in output layout (steer_source == MAP)
     float* out[MARCH_MAX_OUT];
+    // optional fused pyramid emission (whole frames only): next level = cv::pyrDown(input), written from the staged tile
+    float* pyr_out;
+    long long pyr_pitch, pyr_frame_stride;  // bytes
 };
 
 // Tap tables passed BY VALUE as a kernel parameter: they live in the constant bank, so every FFMA takes
@@ -249,6 +252,43 @@ __device__ __forceinline__ void load_tile_manual(float* tile, const MarchArgs& a
 //   basis_row[NBASIS], basis_set[NBASIS], basis_odd[NBASIS]   row plane / column tap set / parity per basis plane
 //   static void epilogue<MASK>(const float (&b)[NBASIS], const MarchArgs&, long long out_off, long long th_off)
 // ------------------------------------------------------------------------------------------------
+// Fused pyramid emission: the next pyramid level (cv::pyrDown of the input: [1 4 6 4 1]^2/256, reflect-101, even samples)
+// for the part of the image this CTA has staged anyway.  The tile's halo (R >= 2) already holds the reflected border, so
+// this costs shared-memory reads and ~4 % more arithmetic instead of a second pass over the input in HBM.
+// CTA region: output rows [yb/2, ceil((yb+nrows)/2)) x output columns [x0/2, x0/2 + 64); thread t takes column t & 63 and
+// the first / second half of the rows (t >> 6), marching with a 5-row window of horizontal sums.
+template <int R, int BH>
+__device__ __forceinline__ void emit_next_level(const float* tile, const MarchArgs& a, int frame, int x0, int yb)
+{
+    constexpr int TWH = march_tile_width(R), HL = march_halo_left(R);
+    int nrows = a.out_row_end - yb;
+    nrows = nrows < BH ? nrows : BH;
+    const int ocols = (a.cols + 1) >> 1;
+    const int xl = threadIdx.x & 63, half = threadIdx.x >> 6;
+    const int xo = (x0 >> 1) + xl;
+    const int nout = (nrows + 1) >> 1;                 // output rows of this CTA (yb is even)
+    const int per = (nout + 1) >> 1;
+    const int ly0 = half * per, ly1 = min(nout, ly0 + per);
+    if (xo >= ocols || ly0 >= ly1) return;
+    const float* tc = tile + 2 * xl + HL;              // tile column of input column 2*xo
+    auto H = [&](int lr) {                             // horizontal 5-tap of input row yb + lr (tile row lr + R)
+        const float* p = tc + (lr + R) * TWH;
+        return dev::pyr_tap5(p[-2], p[-1], p[0], p[1], p[2]);
+    };
+    float* dst = reinterpret_cast<float*>(reinterpret_cast<char*>(a.pyr_out) + (long long)frame * a.pyr_frame_stride +
+                                          (long long)((yb >> 1) + ly0) * a.pyr_pitch) + xo;
+    const long long op = a.pyr_pitch >> 2;
+    int lr = 2 * ly0;
+    float h0 = H(lr - 2), h1 = H(lr - 1), h2 = H(lr);
+    for (int ly = ly0; ly < ly1; ++ly) {
+        const float h3 = H(lr + 1), h4 = H(lr + 2);
+        *dst = dev::pyr_tap5(h0, h1, h2, h3, h4) * (1.f / 256.f);
+        dst += op;
+        h0 = h2, h1 = h3, h2 = h4;
+        lr += 2;
+    }
+}
+
 template <class Fam, unsigned MASK /* 0 = use a.mask at run time */, bool USE_TMA, typename TIn, bool BAKED>
 __global__ void __launch_bounds__(MARCH_TW, Fam::MIN_CTAS)
 k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchArgs a,
@@ -430,6 +470,7 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
             cur.next_row();
         }
     }
+    if (a.pyr_out) emit_next_level<R, BH>(tile, a, frame, x0, yb);  // CTA-uniform; the tile is read-only after staging
 }
 
 }  // namespace cvs

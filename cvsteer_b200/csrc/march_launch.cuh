@@ -168,6 +168,9 @@ static inline MarchArgs make_args(const BatchGeom& g, unsigned mask, const Steer
     a.cos_t = st.cos_t;
     a.sin_t = st.sin_t;
     a.theta_map = st.theta_map;
+    a.pyr_out = g.next_level;
+    a.pyr_pitch = (long long)g.next_pitch;
+    a.pyr_frame_stride = (long long)g.next_frame_stride;
     for (int p = 0; p < nplanes && p < MARCH_MAX_OUT; ++p) a.out[p] = (mask >> p & 1u) ? outs[p] : nullptr;
     return a;
 }

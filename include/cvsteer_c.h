@@ -174,6 +174,11 @@ typedef struct cvs_batch {
      * (y - out_row_origin) of the output planes.  Vertical reflect-101 applies at image rows <0 and
      * >= full_rows only.  For whole frames set full_rows = 0 (=> y_origin 0, all rows). */
     int full_rows, y_origin, out_row_begin, out_row_end, out_row_origin;
+    /* Optional pyramid fusion (whole frames only, i.e. full_rows == 0): when next_level != NULL the SAME launch also
+     * writes the next pyramid level, cv::pyrDown of the input ((cols+1)/2 x (rows+1)/2 per frame, fp32), from the tile it
+     * has staged anyway -- the level never costs a second pass over the input.  Identical bits to cvs_pyr_down_dev. */
+    float* next_level;
+    size_t next_pitch, next_frame_stride;
 } cvs_batch;
 
 CVS_API int cvs_g2_run_batch_dev(cvs_g2* h, const cvs_batch* b, unsigned mask, int steer_source,

@@ -304,3 +304,32 @@ def test_huge_single_image_64bit_indexing():
     assert_close_range(r["strength"][0, H - 100:, 5008:5192].cpu().numpy(), o.strength[20:, 8:-8], rng * rng, "bottom border")
     del r, x
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("shape", [(135, 241), (64, 128), (200, 383), (1080, 1920), (37, 5)])
+def test_fused_pyramid_emission_bitwise(shape):
+    """next_level written by the fused basis kernel == the stand-alone pyr_down kernel, bit for bit; and the pyramid
+    results do not depend on which of the two builds the levels."""
+    fr = _frames(3990, 2, *shape)
+    x = torch.from_numpy(fr).cuda()
+    g = G2Batch()
+    nxt = torch.empty((2, (shape[0] + 1) // 2, (shape[1] + 1) // 2), device="cuda")
+    for mask in (capi.G2_MASK_ORIENT, capi.G2_MASK_STATE, (1 << capi.G2_NPLANES) - 1):
+        nxt.fill_(-1)
+        g.run(x, mask, next_level=nxt)
+        assert torch.equal(nxt, pyr_down(x)), (shape, hex(mask))
+    assert float(np.max(np.abs(nxt[1].cpu().numpy() - ref.pyr_down(fr[1])))) <= 1e-4 * 255
+    a = g.run_pyramid(x, 4, capi.G2_MASK_ORIENT)
+    b = g.run_pyramid(x, 4, capi.G2_MASK_ORIENT, fuse_pyramid=False)
+    for la, lb in zip(a, b):
+        for k in la:
+            assert torch.equal(la[k], lb[k]), k
+    # misaligned input -> LDG loader; generic width -> stand-alone kernel behind the same argument
+    pad = torch.zeros((2, shape[0], shape[1] + 3), device="cuda")
+    pad[:, :, 1:shape[1] + 1] = x
+    nxt.fill_(-1)
+    g.run(pad[:, :, 1:shape[1] + 1], capi.G2_MASK_ORIENT, next_level=nxt)
+    assert torch.equal(nxt, pyr_down(x))
+    nxt.fill_(-1)
+    G2Batch(width=5, spacing=0.5).run(x, capi.G2_MASK_ORIENT, next_level=nxt)
+    assert torch.equal(nxt, pyr_down(x))

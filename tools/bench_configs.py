@@ -65,18 +65,17 @@ def main():
             for _ in range(L - 1):
                 shapes.append(((shapes[-1][0] + 1) // 2, (shapes[-1][1] + 1) // 2))
             outs = [{p: torch.empty((n,) + s, device=dev) for p in (capi.THETA, capi.STRENGTH, capi.E)} for s in shapes]
+            lv = [x] + [torch.empty((n,) + s, device=dev) for s in shapes[1:]]   # every level stays resident
 
             def step():
-                cur = x
+                # one launch per level: the fused kernel also emits the next level from its staged tile
                 for l in range(L):
-                    g.run(cur, capi.G2_MASK_ORIENT, outs=outs[l])
-                    if l + 1 < L:
-                        cur = pyr_down(cur)
+                    g.run(lv[l], capi.G2_MASK_ORIENT, outs=outs[l], next_level=lv[l + 1] if l + 1 < L else None)
             ms = timed(step, a.warmup, a.steps, world, dev)
             px0 = a.frames * R * C
             line = {"config": "cfg3", "what": "G2/H2 M1 over a 5-level pyramid, 3840x2160, %d frames total" % a.frames, "n_gpus": world,
                     "ms_per_step": round(ms, 3), "Mpix_s_level0": round(px0 / 1e6 / (ms / 1e3), 1), "scaling": "strong",
-                    "launches_per_step": 2 * L - 1,
+                    "launches_per_step": L,
                     "algorithmic_GB_s": round(px0 * (1.332 * 16 + 1.328 * 1.25) / 1e9 / (ms / 1e3), 1)}
             del x, outs
         elif cfg == "cfg4":
