@@ -97,6 +97,9 @@ _SIGS = {
     "cvs_g2_run_batch_host_multi": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_int,
                                               C.c_int, C.c_size_t, C.c_size_t, C.c_uint, C.POINTER(C.c_void_p), C.c_size_t,
                                               C.c_size_t]),
+    "cvs_g2_run_bands_host_multi": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_int,
+                                              C.c_size_t, C.c_int, C.c_uint, C.POINTER(C.POINTER(C.c_void_p)),
+                                              C.POINTER(C.c_size_t)]),
     "cvs_bench_ffma": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), _fp]),
     "cvs_g2_last_launch": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                      C.c_char_p, C.c_int]),

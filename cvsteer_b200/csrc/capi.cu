@@ -11,6 +11,7 @@
 #include <new>
 #include <string>
 #include <thread>
+#include <utility>
 #include <vector>
 
 #include "../../include/cvsteer_c.h"
@@ -753,6 +754,149 @@ extern "C" int cvs_g2_run_batch_host_multi(int n_devices, const int* devices, in
             cvs_g2_destroy(h);
         });
     }
+    for (auto& t : threads) t.join();
+    for (int d = 0; d < n_devices; ++d)
+        if (rc[d] != CVS_OK) return fail(rc[d], "device %d: %s", devices ? devices[d] : d, msg[d].c_str());
+    return CVS_OK;
+}
+
+// ---- row bands of one very large image over several GPUs of this process -------------------------------------------
+namespace {
+struct BandPlanC {
+    std::vector<int> rows;                       // image height per level
+    std::vector<std::pair<int, int>> out, have;  // [lo, hi) per level: rows produced / rows that must be resident
+    bool empty() const { return out[0].first >= out[0].second; }
+};
+
+// Same rule as cvsteer_b200/multi.py::plan_bands: band edges on multiples of 2^(levels-1) rows, so that the even-sample
+// pyramid of a band coincides with the pyramid of the whole image; `have` adds the filter halo and the pyr_down support.
+std::vector<BandPlanC> plan_bands_c(int rows, int world, int levels, int radius)
+{
+    const int align = 1 << (levels - 1);
+    std::vector<int> hl(levels);
+    hl[0] = rows;
+    for (int l = 1; l < levels; ++l) hl[l] = (hl[l - 1] + 1) / 2;
+    const int units = (rows + align - 1) / align, per = (units + world - 1) / world;
+    std::vector<int> edges(world + 1);
+    for (int r = 0; r <= world; ++r) edges[r] = std::min<long long>(rows, (long long)r * per * align);
+    edges[world] = rows;
+    std::vector<BandPlanC> plans(world);
+    for (int r = 0; r < world; ++r) {
+        BandPlanC& p = plans[r];
+        p.rows = hl;
+        p.out.resize(levels);
+        p.have.resize(levels);
+        for (int l = 0; l < levels; ++l) {
+            if (edges[r] >= rows) {
+                p.out[l] = {hl[l], hl[l]};
+                continue;
+            }
+            const int lo = std::min(hl[l], edges[r] >> l);
+            const int hi = edges[r + 1] >= rows ? hl[l] : std::min(hl[l], edges[r + 1] >> l);
+            p.out[l] = {lo, std::max(lo, hi)};
+        }
+        for (int l = levels - 1; l >= 0; --l) {
+            std::pair<int, int> need = p.out[l];
+            if (need.first < need.second) need = {std::max(0, need.first - radius), std::min(hl[l], need.second + radius)};
+            if (l + 1 < levels && p.have[l + 1].first < p.have[l + 1].second) {
+                const std::pair<int, int> src = {std::max(0, 2 * p.have[l + 1].first - 2), std::min(hl[l], 2 * (p.have[l + 1].second - 1) + 3)};
+                need = need.first < need.second ? std::make_pair(std::min(need.first, src.first), std::max(need.second, src.second)) : src;
+            }
+            p.have[l] = need;
+        }
+    }
+    return plans;
+}
+
+int run_band_on_device(int device, int width, float spacing, const BandPlanC& plan, const float* image, int cols, size_t step, int levels,
+                       unsigned mask, float* const* const* outs, const size_t* out_steps)
+{
+    if (plan.empty()) return CVS_OK;
+    cvs_g2* hh = nullptr;
+    int rc = cvs_g2_create(&hh, device, width, spacing);
+    if (rc) return rc;
+    Filter* f = reinterpret_cast<Filter*>(hh);
+    auto done = [&](int r) {
+        cvs_g2_destroy(hh);
+        return r;
+    };
+    int nsel = 0;
+    for (int p = 0; p < CVS_G2_NPLANES; ++p) nsel += (mask >> p) & 1u;
+    std::vector<int> lc(levels);
+    lc[0] = cols;
+    for (int l = 1; l < levels; ++l) lc[l] = (lc[l - 1] + 1) / 2;
+    // resident level buffers (rows plan.have[l]) + one output staging area sized for level 0
+    std::vector<DevBuf> lv(levels);
+    std::vector<size_t> pitch(levels);
+    for (int l = 0; l < levels; ++l) {
+        pitch[l] = align_up((size_t)lc[l] * 4, 128);
+        if (cudaError_t e = lv[l].reserve(pitch[l] * (size_t)(plan.have[l].second - plan.have[l].first)); e != cudaSuccess)
+            return done(fail(CVS_ERR_CUDA, "band level %d: %s", l, cudaGetErrorString(e)));
+    }
+    DevBuf stage;
+    if (cudaError_t e = stage.reserve(pitch[0] * (size_t)(plan.out[0].second - plan.out[0].first) * nsel); e != cudaSuccess)
+        return done(fail(CVS_ERR_CUDA, "band outputs: %s", cudaGetErrorString(e)));
+    cudaStream_t s = f->stream;
+    auto cu = [&](cudaError_t e, const char* what) { return e == cudaSuccess ? CVS_OK : fail(CVS_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e)); };
+    rc = cu(cudaMemcpy2DAsync(lv[0].p, pitch[0], reinterpret_cast<const char*>(image) + (size_t)plan.have[0].first * step, step, (size_t)cols * 4,
+                              plan.have[0].second - plan.have[0].first, cudaMemcpyHostToDevice, s),
+            "band upload");
+    for (int l = 0; l < levels && rc == CVS_OK; ++l) {
+        const int lo = plan.out[l].first, hi = plan.out[l].second;
+        if (lo < hi) {
+            BatchGeom g = whole_frame_geom(lv[l].p, false, 1, plan.have[l].second - plan.have[l].first, lc[l], pitch[l], 0, pitch[l], 0);
+            g.full_rows = plan.rows[l];
+            g.y_origin = plan.have[l].first;
+            g.out_row_begin = lo, g.out_row_end = hi, g.out_row_origin = lo;
+            float* d_out[CVS_G2_NPLANES] = {nullptr};
+            int slot = 0;
+            for (int p = 0; p < CVS_G2_NPLANES; ++p)
+                if (mask >> p & 1u) d_out[p] = reinterpret_cast<float*>(static_cast<char*>(stage.p) + (size_t)(slot++) * pitch[l] * (hi - lo));
+            SteerSpec st{};
+            st.source = CVS_STEER_DOMINANT;
+            rc = run_fused(f, g, mask, st, d_out, s);
+            for (int p = 0; p < CVS_G2_NPLANES && rc == CVS_OK; ++p)
+                if (mask >> p & 1u)   // the "gather": each band lands directly in its rows of the caller's full-size plane
+                    rc = cu(cudaMemcpy2DAsync(reinterpret_cast<char*>(outs[l][p]) + (size_t)lo * out_steps[l], out_steps[l], d_out[p], pitch[l],
+                                              (size_t)lc[l] * 4, hi - lo, cudaMemcpyDeviceToHost, s),
+                            "band download");
+        }
+        if (rc == CVS_OK && l + 1 < levels && plan.have[l + 1].first < plan.have[l + 1].second) {
+            BatchGeom g = whole_frame_geom(lv[l].p, false, 1, plan.have[l].second - plan.have[l].first, lc[l], pitch[l], 0, pitch[l + 1], 0);
+            g.full_rows = plan.rows[l];
+            g.y_origin = plan.have[l].first;
+            g.out_row_begin = plan.have[l + 1].first, g.out_row_end = plan.have[l + 1].second, g.out_row_origin = plan.have[l + 1].first;
+            rc = cu(launch_pyr_down(g, static_cast<float*>(lv[l + 1].p), s), "band pyr_down");
+        }
+        // the staging area is reused by the next level: its downloads are ordered on the same stream
+    }
+    if (rc == CVS_OK) rc = cu(cudaStreamSynchronize(s), "band sync");
+    for (auto& b : lv) b.release();
+    stage.release();
+    return done(rc);
+}
+}  // namespace
+
+extern "C" int cvs_g2_run_bands_host_multi(int n_devices, const int* devices, int width, float spacing, const float* image, int rows, int cols,
+                                           size_t step, int levels, unsigned mask, float* const* const* outs, const size_t* out_steps)
+{
+    if (n_devices <= 0 || n_devices > 64 || !image || !outs || !out_steps || rows <= 0 || cols <= 0) return fail(CVS_ERR_INVALID_ARG, "bad argument");
+    if (levels < 1 || levels > 16 || step < (size_t)cols * 4) return fail(CVS_ERR_INVALID_ARG, "levels / step out of range");
+    if (!mask || (mask >> CVS_G2_NPLANES)) return fail(CVS_ERR_INVALID_ARG, "mask 0x%x", mask);
+    for (int l = 0, c = cols; l < levels; ++l, c = (c + 1) / 2) {
+        if (!outs[l] || out_steps[l] < (size_t)c * 4) return fail(CVS_ERR_INVALID_ARG, "outs[%d] / out_steps[%d]", l, l);
+        for (int p = 0; p < CVS_G2_NPLANES; ++p)
+            if ((mask >> p & 1u) && !outs[l][p]) return fail(CVS_ERR_INVALID_ARG, "outs[%d][%d] is null but selected by mask", l, p);
+    }
+    const std::vector<BandPlanC> plans = plan_bands_c(rows, n_devices, levels, width);
+    std::vector<std::thread> threads;
+    std::vector<int> rc(n_devices, CVS_OK);
+    std::vector<std::string> msg(n_devices);
+    for (int d = 0; d < n_devices; ++d)
+        threads.emplace_back([&, d] {
+            rc[d] = run_band_on_device(devices ? devices[d] : d, width, spacing, plans[d], image, cols, step, levels, mask, outs, out_steps);
+            if (rc[d] != CVS_OK) msg[d] = cvs_last_error();
+        });
     for (auto& t : threads) t.join();
     for (int d = 0; d < n_devices; ++d)
         if (rc[d] != CVS_OK) return fail(rc[d], "device %d: %s", devices ? devices[d] : d, msg[d].c_str());

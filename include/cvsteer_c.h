@@ -220,6 +220,16 @@ CVS_API int cvs_g2_run_batch_host_multi(int n_devices, const int* devices, int w
                                         int rows, int cols, size_t in_step, size_t in_frame_stride, unsigned mask,
                                         float* const* outs, size_t out_step, size_t out_frame_stride);
 
+/* One very large image split into ROW BANDS over `n_devices` GPUs of this process.  Band
+ * edges sit on multiples of 2^(levels-1) rows; every GPU uploads its band plus the halo its coarsest level needs straight
+ * from the host image (no halo exchange), builds its slice of the `levels`-level pyramid in band mode, runs the fused
+ * kernel per level and downloads its rows directly into the caller's full-size planes outs[level][plane] (row pitch
+ * out_steps[level]) -- the gather IS the download.  Bit-identical to the single-GPU whole-image pyramid.  The
+ * device-resident variant (outputs gathered to a root GPU with NCCL over NVLink) is cvsteer_b200/multi.py::run_bands. */
+CVS_API int cvs_g2_run_bands_host_multi(int n_devices, const int* devices, int width, float spacing, const float* image,
+                                        int rows, int cols, size_t step, int levels, unsigned mask,
+                                        float* const* const* outs, const size_t* out_steps);
+
 /* ---- measurement helpers (used by bench.py; not part of the reference surface) ---- */
 /* Saturating FFMA loop: returns achieved fp32 instructions/s (1 FFMA = 1 instr = 2 flop).
  * form: 0 = immediate-operand FFMA, 1 = register-operand, 2 = constant-bank operand; 3 = packed FFMA2 (counted as 2 per

@@ -333,3 +333,32 @@ def test_fused_pyramid_emission_bitwise(shape):
     nxt.fill_(-1)
     G2Batch(width=5, spacing=0.5).run(x, capi.G2_MASK_ORIENT, next_level=nxt)
     assert torch.equal(nxt, pyr_down(x))
+
+
+def test_bands_host_multi_equals_whole():
+    """cvs_g2_run_bands_host_multi: one image, row bands over every visible GPU (and over 3 'virtual' bands on one GPU by
+    listing device 0 three times), 4-level pyramid, results identical to the whole-image pyramid."""
+    import ctypes as C
+    H, W, L = 333, 270, 4
+    img = synth(4001, H, W)
+    want = G2Batch().run_pyramid(torch.from_numpy(img[None]).cuda(), L, capi.G2_MASK_ORIENT)
+    planes = [p for p in range(capi.G2_NPLANES) if capi.G2_MASK_ORIENT >> p & 1]
+    shapes = [(H, W)]
+    for _ in range(L - 1):
+        shapes.append(((shapes[-1][0] + 1) // 2, (shapes[-1][1] + 1) // 2))
+    for devs in ([0, 0, 0], list(range(torch.cuda.device_count()))):
+        outs = [{p: np.zeros(s, np.float32) for p in planes} for s in shapes]
+        lvl = (C.POINTER(C.c_void_p) * L)()
+        keep = []
+        for l in range(L):
+            arr = (C.c_void_p * capi.G2_NPLANES)()
+            for p in planes:
+                arr[p] = outs[l][p].ctypes.data
+            keep.append(arr)
+            lvl[l] = C.cast(arr, C.POINTER(C.c_void_p))
+        steps = (C.c_size_t * L)(*[s[1] * 4 for s in shapes])
+        dv = (C.c_int * len(devs))(*devs)
+        capi.check(capi.lib().cvs_g2_run_bands_host_multi(len(devs), dv, 4, 0.67, img.ctypes.data, H, W, W * 4, L, capi.G2_MASK_ORIENT, lvl, steps))
+        for l in range(L):
+            for p in planes:
+                assert np.array_equal(outs[l][p], want[l][capi.G2_PLANE_NAMES[p]][0].cpu().numpy()), (devs, l, p)
