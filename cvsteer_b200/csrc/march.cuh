@@ -164,10 +164,13 @@ struct OutCursor {
     {
         asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %1, 4, %0;\n\tst.global.f32 [a], %2;\n\t}" ::"l"(base[q]), "r"(idx), "f"(v) : "memory");
     }
-    __device__ __forceinline__ float theta(const MarchArgs&) const
+    // steering angle of this thread's pixel `rows_ahead` output rows below the current one
+    __device__ __forceinline__ float theta(const MarchArgs&, int rows_ahead = 0) const
     {
         float v;
-        asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %2, 4, %1;\n\tld.global.nc.f32 %0, [a];\n\t}" : "=f"(v) : "l"(th_base), "r"(idx));
+        asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %2, 4, %1;\n\tld.global.nc.f32 %0, [a];\n\t}"
+                     : "=f"(v)
+                     : "l"(th_base), "r"(idx + (unsigned)rows_ahead * pitch_elems));
         return v;
     }
     __device__ __forceinline__ void next_row() { idx += pitch_elems; }
@@ -181,9 +184,9 @@ struct OutCursor<0u, NPLANES> {  // run-time mask: one shared byte offset, 64-bi
     {
         *reinterpret_cast<float*>(reinterpret_cast<char*>(a.out[q]) + off) = v;
     }
-    __device__ __forceinline__ float theta(const MarchArgs& a) const
+    __device__ __forceinline__ float theta(const MarchArgs& a, int rows_ahead = 0) const
     {
-        return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(a.theta_map) + off);
+        return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(a.theta_map) + off + rows_ahead * pitch);
     }
     __device__ __forceinline__ void next_row() { off += pitch; }
 };
@@ -421,28 +424,33 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
             [&]<int... I>(std::integer_sequence<int, I...>) {
                 ((row_pass(I), col_pass(false, std::integral_constant<int, I>{})), ...);
             }(std::make_integer_sequence<int, 2 * R>{});
+            // (the steering-angle load, if this family reads a map, is issued ahead of the row's arithmetic)
+            float th0 = Fam::template reads_theta_map<MASK>(a) ? cur.theta(a) : 0.f;
             row_pass(2 * R);
             col_pass(true, std::integral_constant<int, 2 * R>{});
-            Fam::template epilogue<MASK>(b, a, cur, 0.f);
+            Fam::template epilogue<MASK>(b, a, cur, th0);
             cur.next_row();
             rt_done = K;
 #pragma unroll 1
             for (; rt_done + K <= total; rt_done += K) {
                 [&]<int... I>(std::integer_sequence<int, I...>) {
-                    ((row_pass(rt_done + I), col_pass(true, std::integral_constant<int, I>{}), Fam::template epilogue<MASK>(b, a, cur, 0.f),
-                      cur.next_row()),
+                    ((th0 = Fam::template reads_theta_map<MASK>(a) ? cur.theta(a) : 0.f, row_pass(rt_done + I),
+                      col_pass(true, std::integral_constant<int, I>{}), Fam::template epilogue<MASK>(b, a, cur, th0), cur.next_row()),
                      ...);
                 }(std::make_integer_sequence<int, K>{});
             }
         }
     }
     int slot = 0;  // rt_done is a multiple of K, so the window slot of tile row rt_done is 0 again
+    float theta_next = 0.f;
+    if (Fam::template reads_theta_map<MASK>(a) && rt_done >= 2 * R && rt_done < nrows + 2 * R) theta_next = cur.theta(a);
 #pragma unroll 1
     for (int rt = rt_done; rt < nrows + 2 * R; ++rt) {
-        // steering-angle map: issue the load for this output row before ~all of the row's arithmetic, so that its DRAM
-        // latency is covered by the row/column passes instead of stalling the epilogue
-        float theta_px = 0.f;
-        if (Fam::template reads_theta_map<MASK>(a) && rt >= 2 * R) theta_px = cur.theta(a);
+        // steering-angle map: the load for an output row is issued ONE ROW AHEAD (during the previous row's arithmetic):
+        // measured on G4 steer, issuing it at the top of its own row still left 25 % of warp samples waiting on it
+        const float theta_px = theta_next;
+        if (Fam::template reads_theta_map<MASK>(a) && rt + 1 >= 2 * R && rt + 1 < nrows + 2 * R)
+            theta_next = cur.theta(a, rt >= 2 * R ? 1 : 0);
         if constexpr (Fam::SHARED_ROW_PASS) row_pass(rt);
 #if CVS_MARCH_TREE_DISPATCH
         dispatch_tree<0, K>(slot, [&](auto slot_c) {
