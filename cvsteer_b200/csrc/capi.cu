@@ -187,6 +187,8 @@ int geom_from_batch(const cvs_batch* b, BatchGeom* g)
     const size_t esz = b->in_is_u8 ? 1 : 4;
     if (b->in_pitch < (size_t)b->cols * esz) return fail(CVS_ERR_INVALID_ARG, "in_pitch %zu < cols*%zu", b->in_pitch, esz);
     if (b->out_pitch < (size_t)b->cols * 4 / 2) return fail(CVS_ERR_INVALID_ARG, "out_pitch too small");
+    if ((b->out_pitch & 3) || (b->out_frame_stride & 3) || (!b->in_is_u8 && ((b->in_pitch & 3) || (b->in_frame_stride & 3) || ((uintptr_t)b->in & 3))))
+        return fail(CVS_ERR_INVALID_ARG, "fp32 planes need 4-byte aligned base, pitch and frame stride");
     *g = whole_frame_geom(b->in, b->in_is_u8 != 0, b->n, b->rows, b->cols, b->in_pitch, b->in_frame_stride, b->out_pitch,
                           b->out_frame_stride);
     if (b->next_level) {

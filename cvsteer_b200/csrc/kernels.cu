@@ -131,9 +131,22 @@ cudaError_t launch_basis_fused(int family, const FamilyTaps& taps, const BatchGe
         }
         return e;
     }
-    if (g.n > 65535) return cudaErrorInvalidValue;  // callers split larger batches
-    return family == 2 ? launch_march_g2(taps, g, a, st.source == CVS_STEER_DOMINANT, stream, info)
-                       : launch_march_g4(taps, g, a, st.source == CVS_STEER_DOMINANT, stream, info);
+    // gridDim.z carries the frame index: batches beyond 65535 frames go out as several launches
+    for (int f0 = 0; f0 < g.n; f0 += 65535) {
+        BatchGeom gc = g;
+        MarchArgs ac = a;
+        gc.n = g.n - f0 < 65535 ? g.n - f0 : 65535;
+        gc.in = static_cast<const char*>(g.in) + (size_t)f0 * g.in_frame_stride;
+        ac.in = gc.in;
+        for (int p = 0; p < MARCH_MAX_OUT; ++p)
+            if (ac.out[p]) ac.out[p] = reinterpret_cast<float*>(reinterpret_cast<char*>(a.out[p]) + (size_t)f0 * g.out_frame_stride);
+        if (ac.theta_map) ac.theta_map = reinterpret_cast<const float*>(reinterpret_cast<const char*>(a.theta_map) + (size_t)f0 * g.out_frame_stride);
+        if (ac.pyr_out) ac.pyr_out = reinterpret_cast<float*>(reinterpret_cast<char*>(a.pyr_out) + (size_t)f0 * g.next_frame_stride);
+        const cudaError_t e = family == 2 ? launch_march_g2(taps, gc, ac, st.source == CVS_STEER_DOMINANT, stream, info)
+                                          : launch_march_g4(taps, gc, ac, st.source == CVS_STEER_DOMINANT, stream, info);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 // ------------------------------------------------------------------------------------------------

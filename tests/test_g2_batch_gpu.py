@@ -362,3 +362,15 @@ def test_bands_host_multi_equals_whole():
         for l in range(L):
             for p in planes:
                 assert np.array_equal(outs[l][p], want[l][capi.G2_PLANE_NAMES[p]][0].cpu().numpy()), (devs, l, p)
+
+
+def test_more_than_65535_frames():
+    """gridDim.z limit: 70000 tiny frames go out as two launches and still match per-frame results."""
+    n = 70000
+    x = torch.rand((n, 6, 8), device="cuda") * 255
+    g = G2Batch()
+    r = g.run(x, capi.G2_MASK_ORIENT)
+    for i in (0, 65534, 65535, 65536, n - 1):
+        one = g.run(x[i:i + 1].contiguous(), capi.G2_MASK_ORIENT)
+        for k in r:
+            assert torch.equal(r[k][i], one[k][0]), (k, i)
