@@ -97,6 +97,30 @@ __device__ __forceinline__ float cv_atan2(float y, float x)
     return a * 0.017453292519943295f;  // (float)(CV_PI/180)
 }
 
+// Fast-path variant for the fused kernels: the same polynomial and quadrant logic as cv_atan2, but with the degree ->
+// radian factor, SteerableFilters::wrap (angles above pi come down by 2 pi) and an optional final scale folded into the
+// constants: returns SCALE * wrap(atan2(y, x)) with SCALE = 1 (phase) or 0.5 (dominant orientation).  Three instructions
+// shorter; differs from the exact sequence by rounding only (~1e-7 rad).
+template <bool HALF>
+__device__ __forceinline__ float cv_atan2_wrapped_fast(float y, float x)
+{
+    constexpr float S = HALF ? 0.5f : 1.0f;
+    constexpr float P1 = 0.9997878412794807f * S, P3 = -0.3258083974640975f * S, P5 = 0.1555786518463281f * S,
+                    P7 = -0.04432655554792128f * S;
+    constexpr float kHalfPi = 1.5707963267948966f * S, kPi = 3.14159265358979f * S, kTwoPi = 6.283185307179586f * S;
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float c = mn * fast_rcp(mx + 2.220446049250313e-16f);
+    const float c2 = c * c;
+    float a = fmaf(fmaf(fmaf(P7, c2, P5), c2, P3), c2, P1) * c;
+    a = (ay > ax) ? kHalfPi - a : a;
+    a = (x < 0.f) ? kPi - a : a;
+    // y < 0: the unwrapped angle is 2 pi - a, which is above pi and wraps to -a  (y == -0 stays at +a, like 360 - 0 = 360 -> 0)
+    a = (y < 0.f) ? ((a == 0.f) ? 0.f : -a) : a;
+    (void)kTwoPi;
+    return a;
+}
+
 // cv::cartToPolar's magnitude: sqrt(x*x + y*y) with the inner sum fused; IEEE sqrt, or MUFU.SQRT when FAST.
 template <bool FAST = false>
 __device__ __forceinline__ float cv_magnitude(float x, float y)
@@ -142,7 +166,8 @@ __device__ __forceinline__ Orientation orientation_g2(float a, float b, float c,
     o.c2 = c2;
     o.c3 = c3;
     o.strength = cv_magnitude<FAST>(c2, c3);
-    o.theta = 0.5f * wrap_pi(cv_atan2<FAST, !FAST>(c3, c2));
+    if (FAST) o.theta = cv_atan2_wrapped_fast<true>(c3, c2);
+    else o.theta = 0.5f * wrap_pi(cv_atan2<false, true>(c3, c2));
     return o;
 }
 
@@ -172,7 +197,7 @@ template <bool FAST = false>
 __device__ __forceinline__ void magnitude_phase(float g, float h, float& mag, float& phase)
 {
     mag = cv_magnitude<FAST>(g, h);
-    const float p = wrap_pi(cv_atan2<FAST, false>(h, g));
+    const float p = FAST ? cv_atan2_wrapped_fast<false>(h, g) : wrap_pi(cv_atan2<false, false>(h, g));
     // cv::patchNaNs: the reference's angle is NaN iff an input is NaN.  One unordered compare of the two inputs
     // (setp.nan is true when either operand is NaN) selects 0.
     asm("{\n\t.reg .pred q;\n\tsetp.nan.f32 q, %1, %2;\n\tselp.f32 %0, 0f00000000, %3, q;\n\t}" : "=f"(phase) : "f"(g), "f"(h), "f"(p));
