@@ -162,7 +162,7 @@ struct OutCursor {
     // recompute that pixel and store the identical value to the identical address.
     __device__ __forceinline__ void put(const MarchArgs&, int q, float v) const
     {
-        asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %1, 4, %0;\n\tst.global.f32 [a], %2;\n\t}" ::"l"(base[q]), "r"(idx), "f"(v) : "memory");
+        asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %1, 4, %0;\n\tst.global.cs.f32 [a], %2;\n\t}" ::"l"(base[q]), "r"(idx), "f"(v) : "memory");
     }
     // steering angle of this thread's pixel `rows_ahead` output rows below the current one
     __device__ __forceinline__ float theta(const MarchArgs&, int rows_ahead = 0) const
@@ -182,7 +182,7 @@ struct OutCursor<0u, NPLANES> {  // run-time mask: one shared byte offset, 64-bi
     __device__ __forceinline__ OutCursor(const MarchArgs& a, long long band_off, int x) : off(band_off + 4ll * x), pitch(a.out_pitch) {}
     __device__ __forceinline__ void put(const MarchArgs& a, int q, float v) const
     {
-        *reinterpret_cast<float*>(reinterpret_cast<char*>(a.out[q]) + off) = v;
+        __stcs(reinterpret_cast<float*>(reinterpret_cast<char*>(a.out[q]) + off), v);
     }
     __device__ __forceinline__ float theta(const MarchArgs& a, int rows_ahead = 0) const
     {
