@@ -101,6 +101,7 @@ struct Filter {
     int device;
     FamilyTaps taps;
     cudaStream_t stream = nullptr;
+    cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};  // H2D / kernel / D2H pipeline of the host-batch call (lazy)
     // resident class state of the last setup()
     int rows = 0, cols = 0;
     size_t pitch = 0;         // bytes, multiple of 128 (TMA needs 16)
@@ -151,6 +152,12 @@ int filter_destroy(Filter* f)
         cudaStreamSynchronize(f->stream);
         cudaStreamDestroy(f->stream);
     }
+    for (cudaStream_t& s : f->pipe)
+        if (s) {
+            cudaStreamSynchronize(s);
+            cudaStreamDestroy(s);
+            s = nullptr;
+        }
     f->in.release();
     f->state.release();
     f->work.release();
@@ -595,7 +602,7 @@ extern "C" int cvs_g2_run_batch_host(cvs_g2* h, const float* in, int n, int rows
     if (chunk < 1) chunk = 1;
     const int NBUF = 3;
     CU_TRY(f->work.reserve((size_t)NBUF * chunk * fbytes * (1 + nout)));
-    static thread_local cudaStream_t streams[NBUF] = {nullptr, nullptr, nullptr};
+    cudaStream_t* streams = f->pipe;  // owned by the handle: they live on the handle's device
     for (int i = 0; i < NBUF; ++i)
         if (!streams[i]) CU_TRY(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking));
     SteerSpec st{};

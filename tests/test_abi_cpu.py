@@ -77,3 +77,12 @@ def test_product_code_never_imports_oracle():
                 src = open(os.path.join(dp, fn)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), fn
                 assert "import cv2" not in src, fn
+
+
+def test_header_is_plain_c_and_c_caller_runs():
+    """include/cvsteer_c.h compiles as pedantic C99 and a C program can call the library (on this CPU box it reaches the
+    no-device error path; on the GPU box tests/test_cpp_dropin_gpu.py runs the same binary against the device)."""
+    import subprocess
+    subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "cpp"), "abi_c_check"], check=True, capture_output=True)
+    r = subprocess.run([os.path.join(ROOT, "tests", "cpp", "abi_c_check")], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)

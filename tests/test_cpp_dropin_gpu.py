@@ -58,3 +58,10 @@ def test_cpp_dropin_reference_flow(fish_fixture, tmp_path):
     assert_close_range(_load(tmp_path, "mag4", shp), w4[2], rng4, "mag4")
     assert_angle_close(_load(tmp_path, "phase4", shp), w4[3], w4[2], 2 * np.pi, "phase4")
     assert_close_range(_load(tmp_path, "g4_s03", shp), o4.steer_scalar(0.3)[0], rng4, "g4 scalar")
+
+
+def test_plain_c_caller_on_gpu():
+    exe = os.path.join(HERE, "cpp", "abi_c_check")
+    assert os.path.exists(exe), "tests/cpp/abi_c_check not built (run __graft_entry__.build())"
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "abi_c ok" in r.stdout, (r.returncode, r.stdout, r.stderr)
