@@ -374,3 +374,21 @@ def test_more_than_65535_frames():
         one = g.run(x[i:i + 1].contiguous(), capi.G2_MASK_ORIENT)
         for k in r:
             assert torch.equal(r[k][i], one[k][0]), (k, i)
+
+
+def test_u8_inputs_on_secondary_paths():
+    """8-bit input through the stand-alone pyr_down kernel and through the generic-width path."""
+    img8 = np.random.default_rng(6).integers(0, 256, (2, 77, 130), dtype=np.uint8)
+    x8, xf = torch.from_numpy(img8).cuda(), torch.from_numpy(img8.astype(np.float32)).cuda()
+    assert torch.equal(pyr_down(x8), pyr_down(xf))
+    g = G2Batch(width=3, spacing=0.8)
+    a, b = g.run(x8, capi.G2_MASK_FULL), g.run(xf, capi.G2_MASK_FULL)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    # non-contiguous (strided) float input view: rows with a pitch larger than cols*4
+    big = torch.rand((2, 77, 200), device="cuda") * 255
+    view = big[:, :, 10:140]
+    r1 = G2Batch().run(view, capi.G2_MASK_ORIENT)
+    r2 = G2Batch().run(view.contiguous(), capi.G2_MASK_ORIENT)
+    for k in r1:
+        assert torch.equal(r1[k], r2[k]), k
