@@ -32,6 +32,10 @@
 #endif
 // 1: the slot dispatch of the rolled loop is a balanced compare tree instead of a switch (which nvcc lowers to a
 // constant-memory jump table: LDC + BRX on the critical path of every row).
+// masks with at most this many planes keep a 64-bit base per plane in registers (2 registers each)
+#ifndef CVS_CURSOR_MAX_PLANES
+#define CVS_CURSOR_MAX_PLANES 8
+#endif
 #ifndef CVS_MARCH_TREE_DISPATCH
 #define CVS_MARCH_TREE_DISPATCH 1
 #endif
@@ -409,7 +413,7 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
     // Output addressing: see OutCursor.
     const long long band_off = (long long)frame * a.out_frame_stride + (long long)(yb - a.out_row_origin) * a.out_pitch;
     // per-plane base registers only pay off while there are few planes (2 registers each); wide masks share one offset
-    OutCursor<(__builtin_popcount(MASK) <= 8 ? MASK : 0u), Fam::NPLANES> cur(a, band_off, x);
+    OutCursor<(__builtin_popcount(MASK) <= CVS_CURSOR_MAX_PLANES ? MASK : 0u), Fam::NPLANES> cur(a, band_off, x);
     int rt_done = 0;  // tile rows already consumed by the unrolled path below (always a multiple of K)
     if constexpr (CVS_MARCH_UNROLL_EPILOGUE && MASK != 0 && !Fam::SHARED_ROW_PASS) {
         // Variant for short epilogues: the whole row body (row pass, column pass, epilogue) is replicated per slot, so the
