@@ -19,10 +19,10 @@ LIB_PATH = os.environ.get("CVS_LIB") or os.path.join(_HERE, "libcvsteer_b200.so"
 G2_NPLANES = 20
 G2_PLANE_NAMES = ("g2a", "g2b", "g2c", "h2a", "h2b", "h2c", "h2d", "c1", "c2", "c3", "theta", "strength",
                   "g2", "h2", "e", "magnitude", "phase", "edges", "lines_dark", "lines_bright")
-(G4A, G4B, G4C, G4D, G4E, H4A, H4B, H4C, H4D, H4E, H4F, G4T, H4T, MAG4, PHASE4) = range(15)
-G4_NPLANES = 15
+(G4A, G4B, G4C, G4D, G4E, H4A, H4B, H4C, H4D, H4E, H4F, G4T, H4T, MAG4, PHASE4, G4_THETA, G4_STRENGTH) = range(17)
+G4_NPLANES = 17
 G4_PLANE_NAMES = ("g4a", "g4b", "g4c", "g4d", "g4e", "h4a", "h4b", "h4c", "h4d", "h4e", "h4f", "g4", "h4",
-                  "magnitude", "phase")
+                  "magnitude", "phase", "theta", "strength")
 
 
 def bit(p):

@@ -38,6 +38,8 @@ void SteerableFiltersG4::setup(const cv::Mat1f& image)
     m_rows = image.rows, m_cols = image.cols;
     cv::Mat1f* p[11] = {&m_g4a, &m_g4b, &m_g4c, &m_g4d, &m_g4e, &m_h4a, &m_h4b, &m_h4c, &m_h4d, &m_h4e, &m_h4f};
     for (int i = 0; i < 11; ++i) *p[i] = cv::Mat1f();  // mirrors are stale until syncHostMirrors()
+    m_theta = cv::Mat1f();
+    m_orientationStrength = cv::Mat1f();
 }
 
 void SteerableFiltersG4::syncHostMirrors() const
@@ -65,6 +67,15 @@ void SteerableFiltersG4::steer(float theta, cv::Mat1f& g4, cv::Mat1f& h4)
     g4.create(m_rows, m_cols);
     h4.create(m_rows, m_cols);
     detail::check(cvs_g4_steer_scalar_host(m_handle, theta, g4.ptr(0), h4.ptr(0), nullptr, nullptr, (size_t)g4.step), "SteerableFiltersG4::steer(float)");
+}
+
+void SteerableFiltersG4::computeDominantOrientation()
+{
+    m_theta.create(m_rows, m_cols);
+    m_orientationStrength.create(m_rows, m_cols);
+    detail::check(cvs_g4_get_plane_host(m_handle, CVS_G4_THETA, m_theta.ptr(0), (size_t)m_theta.step), "SteerableFiltersG4: theta");
+    detail::check(cvs_g4_get_plane_host(m_handle, CVS_G4_STRENGTH, m_orientationStrength.ptr(0), (size_t)m_orientationStrength.step),
+                  "SteerableFiltersG4: strength");
 }
 
 // G4.cpp:88-90 is an empty body; defined here as the G2 class defines it (G2.cpp:107-112)

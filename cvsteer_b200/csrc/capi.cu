@@ -108,6 +108,7 @@ struct Filter {
     DevBuf in, state, work, scratch;
     int nstate = 0;           // planes in `state`: G2 12 (7 basis, c1..c3, theta, strength); G4 11
     bool ready = false;
+    bool g4_orient_ready = false;  // planes 11, 12 of a G4 handle hold theta_d / strength of the current image
     LaunchInfo last{};
 
     float* state_plane(int i) const { return reinterpret_cast<float*>(static_cast<char*>(state.p) + (size_t)i * pitch * rows); }
@@ -133,7 +134,7 @@ int filter_create(Filter** out, int family, int device, int width, float spacing
         if (family == 2) make_taps_g2(s, width, spacing, f->taps.t[s]);
         else make_taps_g4(s, width, spacing, f->taps.t[s]);
     }
-    f->nstate = family == 2 ? 12 : 11;
+    f->nstate = family == 2 ? 12 : 13;  // G4: 11 basis planes + lazily computed theta_d / strength
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
@@ -248,6 +249,7 @@ int filter_setup(Filter* f, const void* image, bool u8, int rows, int cols, size
     if (step < (size_t)cols * esz) return fail(CVS_ERR_INVALID_ARG, "step %zu < cols*%zu", step, esz);
     CU_TRY(cudaSetDevice(f->device));
     f->ready = false;
+    f->g4_orient_ready = false;
     f->rows = rows;
     f->cols = cols;
     f->pitch = align_up((size_t)cols * 4, 128);
@@ -257,7 +259,7 @@ int filter_setup(Filter* f, const void* image, bool u8, int rows, int cols, size
     CU_TRY(cudaMemcpy2DAsync(f->in.p, in_pitch, image, step, (size_t)cols * esz, rows, cudaMemcpyHostToDevice, f->stream));
     BatchGeom g = whole_frame_geom(f->in.p, u8, 1, rows, cols, in_pitch, in_pitch * rows, f->pitch, f->pitch * rows);
     float* outs[MAX_TAPS] = {nullptr};
-    for (int i = 0; i < f->nstate; ++i) outs[i] = f->state_plane(i);
+    for (int i = 0; i < (f->family == 2 ? 12 : 11); ++i) outs[i] = f->state_plane(i);
     SteerSpec st{};
     st.source = CVS_STEER_DOMINANT;
     const unsigned mask = f->family == 2 ? CVS_G2_MASK_STATE : CVS_G4_MASK_BASIS;
@@ -276,12 +278,31 @@ int download(Filter* f, const float* dplane, float* dst, size_t step)
     return CVS_OK;
 }
 
+// G4 only: theta_d / strength are not part of the reference's setup(); computed on first use from the resident basis
+int ensure_g4_orientation(Filter* f)
+{
+    if (f->family != 4 || f->g4_orient_ready) return CVS_OK;
+    PlaneSet ps{};
+    for (int i = 0; i < 11; ++i) ps.p[i] = f->state_plane(i);
+    ps.pitch = f->pitch;
+    CU_TRY(launch_g4_orient_planes(ps, f->rows, f->cols, f->state_plane(11), f->state_plane(12), f->pitch, f->stream));
+    f->g4_orient_ready = true;
+    return CVS_OK;
+}
+
 int filter_get_plane(Filter* f, int plane, float* dst, size_t step)
 {
     if (!f || !dst) return fail(CVS_ERR_INVALID_ARG, "null argument");
     if (!f->ready) return fail(CVS_ERR_NOT_SETUP, "get_plane before setup");
-    if (plane < 0 || plane >= f->nstate) return fail(CVS_ERR_INVALID_ARG, "plane %d not part of the class state", plane);
     CU_TRY(cudaSetDevice(f->device));
+    if (f->family == 4 && (plane == CVS_G4_THETA || plane == CVS_G4_STRENGTH)) {
+        int rc = ensure_g4_orientation(f);
+        if (rc) return rc;
+        plane = plane == CVS_G4_THETA ? 11 : 12;
+    } else if (f->family == 4 && plane >= 11) {
+        return fail(CVS_ERR_INVALID_ARG, "plane %d not part of the class state", plane);
+    }
+    if (plane < 0 || plane >= f->nstate) return fail(CVS_ERR_INVALID_ARG, "plane %d not part of the class state", plane);
     int rc = download(f, f->state_plane(plane), dst, step);
     if (rc) return rc;
     CU_TRY(cudaStreamSynchronize(f->stream));
@@ -315,8 +336,11 @@ int filter_steer(Filter* f, int source, float theta, const float* theta_host, si
                                  f->stream));
         st.theta_map = f->work_plane(5);
     } else {
-        if (f->family != 2) return fail(CVS_ERR_INVALID_ARG, "G4 has no dominant-orientation map (reference: G4.h:40-41 never assigned)");
-        st.theta_map = f->state_plane(CVS_THETA);  // steer(getDominantOrientationAngle(), ...) without a host round trip
+        if (f->family == 4) {  // extension: the reference never assigns G4's m_theta (G4.h:40-41); see CVS_G4_THETA
+            int rc = ensure_g4_orientation(f);
+            if (rc) return rc;
+        }
+        st.theta_map = f->state_plane(f->family == 2 ? (int)CVS_THETA : 11);  // steer(getDominantOrientationAngle(), ...) without a round trip
     }
     float* outs_dev[MARCH_MAX_OUT_HOST] = {nullptr};
     int slot = 0;
@@ -324,7 +348,7 @@ int filter_steer(Filter* f, int source, float theta, const float* theta_host, si
         if (mask >> p & 1u) outs_dev[p] = f->work_plane(slot++);
     if (slot > 5) return fail(CVS_ERR_INVALID_ARG, "too many steer outputs");
     PlaneSet ps{};
-    for (int i = 0; i < f->nstate && i < 16; ++i) ps.p[i] = f->state_plane(i);
+    for (int i = 0; i < (f->family == 2 ? 12 : 11); ++i) ps.p[i] = f->state_plane(i);
     ps.pitch = f->pitch;
     if (f->family == 2)
         CU_TRY(launch_g2_steer_planes(ps, f->rows, f->cols, st, c2t, s2t, th_pitch, mask, outs_dev, f->pitch, f->stream));
@@ -515,7 +539,7 @@ extern "C" int cvs_g4_steer_scalar_host(cvs_g4* h, float theta, float* g4, float
 extern "C" int cvs_g4_steer_map_host(cvs_g4* h, const float* theta, size_t theta_step, float* g4, float* h4, float* magnitude, float* phase,
                                      size_t step)
 {
-    if (!theta) return fail(CVS_ERR_INVALID_ARG, "theta map is null");
+    /* theta == NULL: steer at the handle's own dominant-orientation map (extension, see CVS_G4_THETA) */
     float* outs[CVS_G4_NPLANES] = {nullptr};
     outs[CVS_G4T] = g4, outs[CVS_H4T] = h4, outs[CVS_MAG4] = magnitude, outs[CVS_PHASE4] = phase;
     return filter_steer(reinterpret_cast<Filter*>(h), CVS_STEER_MAP, 0.f, theta, theta_step, g4_steer_mask(g4, h4, magnitude, phase), outs, step);
@@ -538,8 +562,6 @@ static int run_batch_dev(Filter* f, const cvs_batch* b, unsigned mask, int steer
         if ((mask >> p & 1u) && !outs[p]) return fail(CVS_ERR_INVALID_ARG, "outs[%d] is null but selected by mask", p);
     if (steer_source < CVS_STEER_DOMINANT || steer_source > CVS_STEER_MAP) return fail(CVS_ERR_INVALID_ARG, "steer_source %d", steer_source);
     if (steer_source == CVS_STEER_MAP && !theta_map) return fail(CVS_ERR_INVALID_ARG, "theta_map is null");
-    if (f->family == 4 && steer_source == CVS_STEER_DOMINANT && (mask & CVS_G4_MASK_STEER))
-        return fail(CVS_ERR_UNSUPPORTED, "G4 has no dominant orientation; pass a scalar angle or an angle map");
     SteerSpec st{};
     st.source = steer_source;
     st.cos_t = std::cos(theta);

@@ -152,6 +152,36 @@ struct G4Fam {
     __host__ __device__ static constexpr float baked(int set, int i) { constexpr float t[NSETS][R + 1] = CVS_BAKED_G4_TAPS; return t[set][i]; }
 
     static constexpr unsigned kNeedsSteer = CVS_G4_MASK_STEER;
+    static constexpr unsigned kNeedsOrient = CVS_BIT(CVS_G4_THETA) | CVS_BIT(CVS_G4_STRENGTH);
+
+    // C1, C2, C3 of E(theta) = G4(theta)^2 + H4(theta)^2 as quadratic forms of the 11 basis values (coefficients generated
+    // by gen_baked_taps.cpp; zero entries vanish at compile time), then theta_d / strength exactly as the G2 class does.
+    template <bool FAST>
+    __device__ __forceinline__ static dev::Orientation orientation(const float (&b)[NBASIS])
+    {
+        constexpr float Q[3][36] = CVS_G4_ORIENT_FORMS;
+        float c[3] = {0.f, 0.f, 0.f};
+        int e = 0;
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {
+            const int n = blk == 0 ? 5 : 6, o = blk == 0 ? 0 : 5;
+#pragma unroll
+            for (int i = 0; i < n; ++i)
+#pragma unroll
+                for (int j = i; j < n; ++j, ++e) {
+                    const float p = b[o + i] * b[o + j];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                        if (Q[k][e] != 0.f) c[k] = fmaf(Q[k][e], p, c[k]);
+                }
+        }
+        dev::Orientation r;
+        r.c1 = c[0], r.c2 = c[1], r.c3 = c[2];
+        r.strength = dev::cv_magnitude<FAST>(c[1], c[2]);
+        if (FAST) r.theta = dev::cv_atan2_wrapped_fast<true>(c[2], c[1]);
+        else r.theta = 0.5f * dev::wrap_pi(dev::cv_atan2<false, true>(c[2], c[1]));
+        return r;
+    }
     // static steer masks are only dispatched for map steering (march_g4.cu)
     template <unsigned MASK>
     __device__ __forceinline__ static bool reads_theta_map(const MarchArgs& a)
@@ -160,6 +190,7 @@ struct G4Fam {
     }
 
     // MASK != 0: compile-time plane set, steering at a per-pixel angle map (config 4), SFU approximations.
+    // MASK == 0: run-time mask; steering at a scalar angle, an angle map, or the in-kernel dominant angle.
     template <unsigned MASK, class Cursor>
     __device__ __forceinline__ static void epilogue(const float (&b)[NBASIS], const MarchArgs& a, const Cursor& cur, float theta_px)
     {
@@ -169,6 +200,14 @@ struct G4Fam {
 #pragma unroll
         for (int q = 0; q < NBASIS; ++q)
             if (m & (1u << q)) put(q, b[q]);
+        if (!(m & (kNeedsSteer | kNeedsOrient))) return;
+        const bool dominant = !MASK && a.steer_source == CVS_STEER_DOMINANT;
+        if ((m & kNeedsOrient) || (dominant && (m & kNeedsSteer))) {
+            const dev::Orientation o = orientation<FAST>(b);
+            if (m & CVS_BIT(CVS_G4_THETA)) put(CVS_G4_THETA, o.theta);
+            if (m & CVS_BIT(CVS_G4_STRENGTH)) put(CVS_G4_STRENGTH, o.strength);
+            if (dominant) theta_px = o.theta;
+        }
         if (!(m & kNeedsSteer)) return;
         float ct, st;
         if (!MASK && a.steer_source == CVS_STEER_SCALAR) {

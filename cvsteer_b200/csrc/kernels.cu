@@ -231,6 +231,34 @@ __global__ void k_g4_steer_planes(const __grid_constant__ PlaneSteerArgs a)
     }
 }
 
+// G4 orientation analysis on the stored basis planes (class API: getters / steer at the dominant angle)
+__global__ void k_g4_orient_planes(const __grid_constant__ PlaneSteerArgs a)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= a.cols) return;
+    float b[11];
+#pragma unroll
+    for (int q = 0; q < 11; ++q) b[q] = at(a.p[q], a.pitch, y, x);
+    const dev::Orientation o = G4Fam::orientation<false>(b);
+    at(a.out[CVS_G4_THETA], a.out_pitch, y, x) = o.theta;
+    at(a.out[CVS_G4_STRENGTH], a.out_pitch, y, x) = o.strength;
+}
+
+cudaError_t launch_g4_orient_planes(const PlaneSet& basis, int rows, int cols, float* theta, float* strength, size_t out_pitch, cudaStream_t stream)
+{
+    PlaneSteerArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int i = 0; i < 16; ++i) a.p[i] = basis.p[i];
+    a.pitch = (long long)basis.pitch;
+    a.out_pitch = (long long)out_pitch;
+    a.rows = rows, a.cols = cols;
+    a.out[CVS_G4_THETA] = theta;
+    a.out[CVS_G4_STRENGTH] = strength;
+    k_g4_orient_planes<<<dim3((cols + 127) / 128, rows), 128, 0, stream>>>(a);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
 static PlaneSteerArgs make_psa(const PlaneSet& ps, int rows, int cols, const SteerSpec& st, float c2t, float s2t, size_t theta_pitch,
                                unsigned mask, float* const* outs, size_t out_pitch, int nplanes)
 {

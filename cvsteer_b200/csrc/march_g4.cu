@@ -5,8 +5,7 @@ namespace cvs {
 
 cudaError_t launch_march_g4(const FamilyTaps& taps, const BatchGeom& g, const MarchArgs& a, bool dom, cudaStream_t stream, LaunchInfo* info)
 {
-    // the reference has no G4 orientation analysis (G4.h:40-41,55): there is no dominant angle to steer to
-    if (dom && (a.mask & G4Fam::kNeedsSteer)) return cudaErrorInvalidValue;
+    (void)dom;  // dominant-angle steering runs in the run-time-mask kernel (orientation analysis in the epilogue)
     TapTable<G4Fam::NSETS, G4Fam::R> tt;
     fill_tap_table<G4Fam>(taps, tt);
     const int out_rows = g.out_row_end - g.out_row_begin;

@@ -181,12 +181,23 @@ class SteerableFiltersG4(_Base):
             return self.plane(capi.G4_PLANE_NAMES.index(name))
         raise AttributeError(name)
 
+    # Extension (the reference declares these getters but never assigns the members, G4.h:40-41,55): lowest-order
+    # Fourier terms of G4(theta)^2 + H4(theta)^2, the definition the reference uses for G2 -- see CVS_G4_THETA.
+    def getDominantOrientationAngle(self):
+        return self.plane(capi.G4_THETA)
+
+    def getDominantOrientationStrength(self):
+        return self.plane(capi.G4_STRENGTH)
+
     def steer(self, theta, with_phase: bool = False):
-        """steer(float | Mat1f theta, g4, h4), G4.h:45-46; with_phase adds (magnitude, phase) per the G2 definition."""
+        """steer(float | Mat1f theta, g4, h4), G4.h:45-46; with_phase adds (magnitude, phase) per the G2 definition.
+        theta=None steers at the handle's own dominant-orientation map (extension)."""
         outs = self._new(4 if with_phase else 2)
         ptrs = [_ptr(o) for o in outs] + [None] * (4 - len(outs))
         step = outs[0].strides[0]
-        if isinstance(theta, np.ndarray):
+        if theta is None:
+            capi.check(self._lib.cvs_g4_steer_map_host(self._h, None, 0, *ptrs, step))
+        elif isinstance(theta, np.ndarray):
             th = _f32c(theta, "theta")
             if th.shape != (self.rows, self.cols):
                 raise capi.CvsError(capi.ERR_SIZE_MISMATCH, f"theta {th.shape} vs image {(self.rows, self.cols)}")

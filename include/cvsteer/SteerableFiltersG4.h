@@ -27,6 +27,11 @@ public:
     void steer(float theta, cv::Mat1f& g4, cv::Mat1f& h4);
     void computeMagnitudeAndPhase(const cv::Mat1f& g4, const cv::Mat1f& h4, cv::Mat1f& magnitude, cv::Mat1f& phase);
 
+    // Extension (not in the reference, whose getters above stay empty because m_theta / m_orientationStrength are never
+    // assigned): fills them with the dominant orientation of the G4/H4 oriented energy, defined like the G2 class's
+    // (lowest-order Fourier terms of G4(theta)^2 + H4(theta)^2); see CVS_G4_THETA in cvsteer_c.h.
+    void computeDominantOrientation();
+
 protected:
     void syncHostMirrors() const;
 

@@ -75,7 +75,13 @@ typedef enum cvs_g4_plane {
     CVS_H4T = 12,      /* H4 steered  G4.cpp:111 / :121 */
     CVS_MAG4 = 13,     /* sqrt(g4^2+h4^2): the reference's G4 computeMagnitudeAndPhase is empty */
     CVS_PHASE4 = 14,   /* (G4.cpp:88-90); defined as the G2 class's (G2.cpp:107-112) on (g4,h4) */
-    CVS_G4_NPLANES = 15
+    /* G4 orientation analysis -- NOT in the reference (m_theta / m_orientationStrength are declared but never assigned,
+     * G4.h:40-41,55).  Defined here exactly as the reference defines it for G2: the lowest-order Fourier terms of the
+     * oriented energy E(theta) = G4(theta)^2 + H4(theta)^2 ~ C1 + C2 cos 2theta + C3 sin 2theta, theta_d = atan2(C3,C2)/2,
+     * strength = |(C2,C3)|; the same derivation reproduces the G2 constants of G2.cpp:93-95 exactly. */
+    CVS_G4_THETA = 15,
+    CVS_G4_STRENGTH = 16,
+    CVS_G4_NPLANES = 17
 } cvs_g4_plane;
 #define CVS_G4_MASK_BASIS 0x000007FFu
 #define CVS_G4_MASK_STEER (CVS_BIT(CVS_G4T) | CVS_BIT(CVS_H4T) | CVS_BIT(CVS_MAG4) | CVS_BIT(CVS_PHASE4))
@@ -83,7 +89,7 @@ typedef enum cvs_g4_plane {
 /* Which angle the fused kernels steer to. */
 typedef enum cvs_steer_source {
     CVS_STEER_DOMINANT = 0, /* per-pixel theta_d computed in the same kernel (what both reference callers do:
-                               example/steer.cpp:87, test/test.cpp:86).  G2 only. */
+                               example/steer.cpp:87, test/test.cpp:86); for G4 see CVS_G4_THETA. */
     CVS_STEER_SCALAR = 1,   /* one angle for the image   steer(float theta, ...)  G2.cpp:137, G4.cpp:114 */
     CVS_STEER_MAP = 2       /* per-pixel angle map       steer(const Mat1f& theta, ...) G2.cpp:147, G4.cpp:92 */
 } cvs_steer_source;
@@ -144,7 +150,7 @@ CVS_API int cvs_g4_create(cvs_g4** out, int device, int width, float spacing);  
 CVS_API int cvs_g4_destroy(cvs_g4* h);
 CVS_API int cvs_g4_setup_host(cvs_g4* h, const float* image, int rows, int cols, size_t step); /* G4.cpp:67-81 */
 CVS_API int cvs_g4_size(const cvs_g4* h, int* rows, int* cols);
-CVS_API int cvs_g4_get_plane_host(cvs_g4* h, int plane, float* dst, size_t step);  /* CVS_G4A..CVS_H4F */
+CVS_API int cvs_g4_get_plane_host(cvs_g4* h, int plane, float* dst, size_t step);  /* CVS_G4A..CVS_H4F, CVS_G4_THETA, CVS_G4_STRENGTH */
 /* steer(float theta, g4, h4) G4.cpp:114-122; magnitude/phase optional (see CVS_MAG4) */
 CVS_API int cvs_g4_steer_scalar_host(cvs_g4* h, float theta, float* g4, float* h4, float* magnitude,
                                      float* phase, size_t step);

@@ -77,6 +77,9 @@ int main(int argc, char** argv)
         filters4.steer(0.3f, g4s, h4s);
         save(dir, "g4_s03", g4s);
         if (!filters4.getDominantOrientationAngle().empty()) return 5;  // never assigned in the reference either
+        filters4.computeDominantOrientation();                          // extension
+        save(dir, "theta4", filters4.getDominantOrientationAngle());
+        save(dir, "strength4", filters4.getDominantOrientationStrength());
 
         // --- error behaviour: a failing C-ABI call surfaces as cv::Exception, like OpenCV's CV_Assert would
         bool threw = false;

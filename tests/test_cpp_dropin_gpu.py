@@ -58,6 +58,11 @@ def test_cpp_dropin_reference_flow(fish_fixture, tmp_path):
     assert_close_range(_load(tmp_path, "mag4", shp), w4[2], rng4, "mag4")
     assert_angle_close(_load(tmp_path, "phase4", shp), w4[3], w4[2], 2 * np.pi, "phase4")
     assert_close_range(_load(tmp_path, "g4_s03", shp), o4.steer_scalar(0.3)[0], rng4, "g4 scalar")
+    # extension: computeDominantOrientation() == the Python class's getters (same C-ABI call)
+    import cvsteer_b200 as cb
+    f4 = cb.SteerableFiltersG4(fish.astype(np.float32))
+    assert np.array_equal(_load(tmp_path, "theta4", shp), f4.getDominantOrientationAngle())
+    assert np.array_equal(_load(tmp_path, "strength4", shp), f4.getDominantOrientationStrength())
 
 
 def test_plain_c_caller_on_gpu():
