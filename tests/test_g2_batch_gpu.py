@@ -392,3 +392,50 @@ def test_u8_inputs_on_secondary_paths():
     r2 = G2Batch().run(view.contiguous(), capi.G2_MASK_ORIENT)
     for k in r1:
         assert torch.equal(r1[k], r2[k]), k
+
+
+def test_fuzz_shapes_masks_vs_oracle():
+    """Seeded fuzz over image shapes around every tiling boundary (strip width 128, band height 64, row groups of 9),
+    output masks and steering modes; every selected plane is compared with the oracle."""
+    rs = np.random.default_rng(20261017)
+    edge_rows = [1, 2, 4, 5, 8, 9, 10, 55, 56, 57, 63, 64, 65, 72, 73, 127, 128, 129, 136]
+    edge_cols = [1, 3, 4, 5, 9, 120, 124, 127, 128, 129, 132, 133, 255, 256, 257, 260, 391]
+    g = G2Batch()
+    for it in range(28):
+        rows = int(rs.choice(edge_rows)) if it % 3 else int(rs.integers(1, 200))
+        cols = int(rs.choice(edge_cols)) if it % 2 else int(rs.integers(1, 420))
+        n = int(rs.integers(1, 4))
+        fr = np.stack([synth(9000 + 10 * it + i, rows, cols) for i in range(n)])
+        mode = it % 4
+        x = torch.from_numpy(fr).cuda()
+        if mode == 0:
+            mask, kw = capi.G2_MASK_FULL, {}
+        elif mode == 1:
+            mask, kw = capi.G2_MASK_STATE, {}
+        elif mode == 2:
+            mask = capi.G2_MASK_ORIENT | capi.bit(capi.G2A) | capi.bit(capi.H2D) | capi.bit(capi.G2T) | capi.bit(capi.PHASE) | capi.bit(capi.MAG)
+            kw = {}
+        else:
+            mask = capi.bit(capi.G2T) | capi.bit(capi.H2T) | capi.bit(capi.E) | capi.bit(capi.MAG)
+            kw = dict(steer=capi.STEER_SCALAR, theta=float(rs.uniform(-3, 3)))
+        r = g.run(x, mask, **kw)
+        for i in range(n):
+            o = ref.SteerableFiltersG2(fr[i])
+            rng = max(basis_range([getattr(o, k) for k in STATE]), 1.0)
+            tag = f"it{it} {rows}x{cols} f{i} "
+            for k in STATE + ("c1", "c2", "c3", "strength"):
+                if k in r:
+                    assert_close_range(r[k][i].cpu().numpy(), getattr(o, k), rng if k in STATE else rng * rng, tag + k)
+            if "theta" in r:
+                assert_angle_close(r["theta"][i].cpu().numpy(), o.theta, o.strength, np.pi, tag + "theta")
+            if mode == 3:
+                w = o.steer_scalar_full(kw["theta"])
+            elif "g2" in r or "phase" in r or "magnitude" in r:
+                w = o.steer_map_full(r["theta"][i].cpu().numpy())
+            else:
+                continue
+            for k, j, s in (("g2", 0, rng), ("h2", 1, rng), ("e", 2, rng * rng), ("magnitude", 3, rng)):
+                if k in r and not (k == "e" and mode == 1):
+                    assert_close_range(r[k][i].cpu().numpy(), w[j], s, tag + k)
+            if "phase" in r:
+                assert_angle_close(r["phase"][i].cpu().numpy(), w[4], w[3], 2 * np.pi, tag + "phase")
