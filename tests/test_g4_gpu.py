@@ -150,3 +150,26 @@ def test_g4_dominant_orientation_extension():
         t2 = cb.SteerableFiltersG2(gr).getDominantOrientationAngle()[30:-30, 30:-30]
         d = np.abs(t4 - t2) % np.pi
         assert float(np.median(np.minimum(d, np.pi - d))) < 0.02, ang
+
+
+def test_g4_flip_symmetry_and_crop_parity_4k():
+    """Config-4 frame size (3840x2160): size-independent properties of the G4/H4 basis (a horizontal flip mirrors the
+    planes whose row filter is even and negates those whose row filter is odd, exactly), plus oracle parity on a crop."""
+    rs = np.random.default_rng(321)
+    img = rs.uniform(0, 255, (1, 2160, 3840)).astype(np.float32)
+    g = G4Batch()
+    x = torch.from_numpy(img).cuda()
+    a = g.run(x, capi.G4_MASK_BASIS)
+    b = g.run(torch.flip(x, dims=[2]).contiguous(), capi.G4_MASK_BASIS)
+    sign = {"g4a": 1, "g4b": -1, "g4c": 1, "g4d": -1, "g4e": 1, "h4a": -1, "h4b": 1, "h4c": -1, "h4d": 1, "h4e": -1, "h4f": 1}
+    for k, s in sign.items():
+        assert torch.equal(torch.flip(b[k], dims=[2]), s * a[k]), k
+    o = ref.SteerableFiltersG4(img[0, 900:1100, 1500:1800])
+    rng = basis_range([getattr(o, k) for k in P])
+    for k in P:
+        assert_close_range(a[k][0, 912:1088, 1512:1788].cpu().numpy(), getattr(o, k)[12:-12, 12:-12], rng, "crop " + k)
+    th = torch.rand((1, 2160, 3840), device="cuda") * 3 - 1.5
+    r = g.run(x, capi.G4_MASK_STEER, steer=capi.STEER_MAP, theta_map=th)
+    w = o.steer_map_full(th[0, 900:1100, 1500:1800].cpu().numpy())
+    assert_close_range(r["g4"][0, 912:1088, 1512:1788].cpu().numpy(), w[0][12:-12, 12:-12], rng, "crop g4")
+    assert_close_range(r["magnitude"][0, 912:1088, 1512:1788].cpu().numpy(), w[2][12:-12, 12:-12], rng, "crop magnitude")
