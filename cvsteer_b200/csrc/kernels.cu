@@ -369,7 +369,7 @@ __global__ void k_pyr_down(const __grid_constant__ MarchArgs a, float* out, int 
 // register window of the horizontal results; every second input row it emits one output.  All loads of an iteration
 // (4 input rows = 2 outputs) are issued before any arithmetic so that ~80 B per thread are in flight: the kernel is
 // HBM-bound (reads every input pixel once, writes a quarter).  Same arithmetic order as k_pyr_down.
-enum { PD_ROWS = 32, PD_THREADS = 128 };
+enum { PD_ROWS = 16, PD_THREADS = 128 };
 
 __global__ void __launch_bounds__(PD_THREADS) k_pyr_down_march(const __grid_constant__ MarchArgs a, float* out, int out_cols)
 {
@@ -386,18 +386,22 @@ __global__ void __launch_bounds__(PD_THREADS) k_pyr_down_march(const __grid_cons
         xs0 = dev::reflect101(xc - 2, a.cols), xs1 = dev::reflect101(xc - 1, a.cols);
         xs3 = dev::reflect101(xc + 1, a.cols), xs4 = dev::reflect101(xc + 2, a.cols);
     }
-    // horizontal 5-tap of image row y (reflected), OpenCV order: 6*c + 4*(l1+r1) + l2 + r2
+    // Rows: bands that stay clear of the top/bottom image border (CTA-uniform test) address rows directly, so the loop
+    // body is branch-free and all of an iteration's loads issue back to back; border bands fold rows with reflect-101.
+    const bool rows_interior = (2 * yo0 - 2 >= 0) && (2 * (yo1 - 1) + 2 < a.full_rows);
+    const long long pitch_f = a.in_pitch >> 2;
+    const float* img0 = reinterpret_cast<const float*>(base) - (long long)a.y_origin * pitch_f;  // row y lives at img0 + y * pitch_f
     auto load_row = [&](int y, float2& p, float2& q, float& e) {
-        const int gy = dev::reflect101(y, a.full_rows) - a.y_origin;
-        const float* src = reinterpret_cast<const float*>(base + (long long)gy * a.in_pitch);
+        const int gy = rows_interior ? y : dev::reflect101(y, a.full_rows);
+        const float* src = img0 + (long long)gy * pitch_f;
         if (interior) {
-            p = *reinterpret_cast<const float2*>(src + xc - 2);
-            q = *reinterpret_cast<const float2*>(src + xc);
-            e = src[xc + 2];
+            p = __ldg(reinterpret_cast<const float2*>(src + xc - 2));
+            q = __ldg(reinterpret_cast<const float2*>(src + xc));
+            e = __ldg(src + xc + 2);
         } else {
-            p = make_float2(src[xs0], src[xs1]);
-            q = make_float2(src[xc], src[xs3]);
-            e = src[xs4];
+            p = make_float2(__ldg(src + xs0), __ldg(src + xs1));
+            q = make_float2(__ldg(src + xc), __ldg(src + xs3));
+            e = __ldg(src + xs4);
         }
     };
     auto hsum = [](const float2& p, const float2& q, float e) { return dev::pyr_tap5(p.x, p.y, q.x, q.y, e); };
