@@ -73,9 +73,14 @@ extern "C" int cvs_g4_make_taps(int which, int width, float spacing, float* dst)
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-struct DevBuf {
+struct DevBuf {  // owning device allocation that only ever grows; freed on release() or destruction
     void* p = nullptr;
     size_t bytes = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr, o.bytes = 0; }
+    ~DevBuf() { release(); }
     cudaError_t reserve(size_t n)
     {
         if (n <= bytes) return cudaSuccess;
@@ -560,6 +565,7 @@ static int run_batch_dev(Filter* f, const cvs_batch* b, unsigned mask, int steer
     if (!outs) return fail(CVS_ERR_INVALID_ARG, "outs is null");
     for (int p = 0; p < nplanes; ++p)
         if ((mask >> p & 1u) && !outs[p]) return fail(CVS_ERR_INVALID_ARG, "outs[%d] is null but selected by mask", p);
+    if (b->out_pitch < (size_t)b->cols * 4) return fail(CVS_ERR_INVALID_ARG, "out_pitch %zu < cols*4", b->out_pitch);
     if (steer_source < CVS_STEER_DOMINANT || steer_source > CVS_STEER_MAP) return fail(CVS_ERR_INVALID_ARG, "steer_source %d", steer_source);
     if (steer_source == CVS_STEER_MAP && !theta_map) return fail(CVS_ERR_INVALID_ARG, "theta_map is null");
     SteerSpec st{};
