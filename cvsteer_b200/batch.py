@@ -162,6 +162,20 @@ class G4Batch(_FusedBatch):
     def __init__(self, width: int = 6, spacing: float = 0.5, device: Optional[int] = None):
         super().__init__(width, spacing, device)
 
+    def run_host(self, frames_host: torch.Tensor, mask: int, outs_host: Dict[int, torch.Tensor],
+                 theta: Optional[float] = None):
+        """End-to-end host-buffer call (cvs_g4_run_batch_host).  theta=None steers at the G4 theta_d."""
+        x = frames_host
+        n, rows, cols = x.shape
+        arr = (C.c_void_p * capi.G4_NPLANES)()
+        for p, t in outs_host.items():
+            arr[p] = t.data_ptr()
+        any_out = next(iter(outs_host.values()))
+        src = capi.STEER_DOMINANT if theta is None else capi.STEER_SCALAR
+        capi.check(self._lib.cvs_g4_run_batch_host(self._h, C.c_void_p(x.data_ptr()), n, rows, cols, x.stride(1) * 4,
+                                                   x.stride(0) * 4, mask, src, float(theta or 0.0), arr,
+                                                   any_out.stride(1) * 4, any_out.stride(0) * 4))
+
 
 def pyr_down(frames: torch.Tensor, band: Optional[Band] = None, out_rows: Optional[range] = None,
              stream=None) -> torch.Tensor:

@@ -607,16 +607,19 @@ extern "C" int cvs_pyr_down_dev(int device, const cvs_batch* b, float* out, void
 
 // Host-buffer batch: frames are processed in chunks on two streams so that the upload of chunk i+1, the kernel of
 // chunk i and the download of chunk i-1 overlap.
-extern "C" int cvs_g2_run_batch_host(cvs_g2* h, const float* in, int n, int rows, int cols, size_t in_step, size_t in_frame_stride,
-                                     unsigned mask, float* const* outs, size_t out_step, size_t out_frame_stride)
+namespace {
+int run_batch_host(Filter* f, int family, const float* in, int n, int rows, int cols, size_t in_step, size_t in_frame_stride, unsigned mask,
+                   int steer_source, float theta, float* const* outs, size_t out_step, size_t out_frame_stride)
 {
-    Filter* f = reinterpret_cast<Filter*>(h);
-    if (!f || !in || !outs) return fail(CVS_ERR_INVALID_ARG, "null argument");
+    if (!f || f->family != family || !in || !outs) return fail(CVS_ERR_INVALID_ARG, "null argument or wrong handle family");
+    const int NPLANES = family == 2 ? (int)CVS_G2_NPLANES : (int)CVS_G4_NPLANES;
+    if (steer_source != CVS_STEER_DOMINANT && steer_source != CVS_STEER_SCALAR)
+        return fail(CVS_ERR_INVALID_ARG, "host batches steer at theta_d or at one scalar angle (steer_source %d)", steer_source);
     if (n <= 0 || rows <= 0 || cols <= 0) return fail(CVS_ERR_INVALID_ARG, "n/rows/cols must be positive");
     if (in_step < (size_t)cols * 4 || out_step < (size_t)cols * 4) return fail(CVS_ERR_INVALID_ARG, "step < cols*4");
-    if (!mask || (mask >> CVS_G2_NPLANES)) return fail(CVS_ERR_INVALID_ARG, "mask 0x%x", mask);
+    if (!mask || (mask >> NPLANES)) return fail(CVS_ERR_INVALID_ARG, "mask 0x%x", mask);
     int nout = 0;
-    for (int p = 0; p < CVS_G2_NPLANES; ++p)
+    for (int p = 0; p < NPLANES; ++p)
         if (mask >> p & 1u) {
             if (!outs[p]) return fail(CVS_ERR_INVALID_ARG, "outs[%d] is null but selected by mask", p);
             ++nout;
@@ -634,7 +637,9 @@ extern "C" int cvs_g2_run_batch_host(cvs_g2* h, const float* in, int n, int rows
     for (int i = 0; i < NBUF; ++i)
         if (!streams[i]) CU_TRY(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking));
     SteerSpec st{};
-    st.source = CVS_STEER_DOMINANT;
+    st.source = steer_source;
+    st.cos_t = std::cos(theta);
+    st.sin_t = std::sin(theta);
     int ci = 0;
     for (int f0 = 0; f0 < n; f0 += chunk, ++ci) {
         const int nf = (n - f0 < chunk) ? (n - f0) : chunk;
@@ -657,14 +662,14 @@ extern "C" int cvs_g2_run_batch_host(cvs_g2* h, const float* in, int n, int rows
                                          reinterpret_cast<const char*>(in) + (size_t)(f0 + k) * in_frame_stride, in_step, (size_t)cols * 4,
                                          rows, cudaMemcpyHostToDevice, s));
         }
-        float* douts[CVS_G2_NPLANES] = {nullptr};
+        float* douts[(int)CVS_G2_NPLANES > (int)CVS_G4_NPLANES ? (int)CVS_G2_NPLANES : (int)CVS_G4_NPLANES] = {nullptr};
         int slot = 0;
-        for (int p = 0; p < CVS_G2_NPLANES; ++p)
+        for (int p = 0; p < NPLANES; ++p)
             if (mask >> p & 1u) douts[p] = reinterpret_cast<float*>(base + (size_t)(1 + slot++) * chunk * fbytes);
         BatchGeom g = whole_frame_geom(din, false, nf, rows, cols, pitch, fbytes, pitch, fbytes);
         int rc = run_fused(f, g, mask, st, douts, s);
         if (rc) return rc;
-        for (int p = 0; p < CVS_G2_NPLANES; ++p)
+        for (int p = 0; p < NPLANES; ++p)
             if (mask >> p & 1u) {
                 char* dst = reinterpret_cast<char*>(outs[p]) + (size_t)f0 * out_frame_stride;
                 if (out_frame_stride % out_step == 0) {
@@ -683,6 +688,21 @@ extern "C" int cvs_g2_run_batch_host(cvs_g2* h, const float* in, int n, int rows
     }
     for (int i = 0; i < NBUF; ++i) CU_TRY(cudaStreamSynchronize(streams[i]));
     return CVS_OK;
+}
+}  // namespace
+
+extern "C" int cvs_g2_run_batch_host(cvs_g2* h, const float* in, int n, int rows, int cols, size_t in_step, size_t in_frame_stride,
+                                     unsigned mask, float* const* outs, size_t out_step, size_t out_frame_stride)
+{
+    return run_batch_host(reinterpret_cast<Filter*>(h), 2, in, n, rows, cols, in_step, in_frame_stride, mask, CVS_STEER_DOMINANT, 0.f, outs,
+                          out_step, out_frame_stride);
+}
+extern "C" int cvs_g4_run_batch_host(cvs_g4* h, const float* in, int n, int rows, int cols, size_t in_step, size_t in_frame_stride,
+                                     unsigned mask, int steer_source, float theta_scalar, float* const* outs, size_t out_step,
+                                     size_t out_frame_stride)
+{
+    return run_batch_host(reinterpret_cast<Filter*>(h), 4, in, n, rows, cols, in_step, in_frame_stride, mask, steer_source, theta_scalar, outs,
+                          out_step, out_frame_stride);
 }
 
 extern "C" int cvs_to_u8_dev(int device, const float* src, int n, int rows, int cols, size_t pitch, size_t frame_stride, float gain, uint8_t* dst,
@@ -705,7 +725,7 @@ extern "C" int cvs_g2_lines_u8_host(cvs_g2* h, const uint8_t* gray, int n, int r
 {
     Filter* f = reinterpret_cast<Filter*>(h);
     if (!f || f->family != 2 || !gray) return fail(CVS_ERR_INVALID_ARG, "null argument");
-    if (n <= 0 || rows <= 0 || cols <= 0 || n > 65535) return fail(CVS_ERR_INVALID_ARG, "n/rows/cols out of range");
+    if (n <= 0 || rows <= 0 || cols <= 0) return fail(CVS_ERR_INVALID_ARG, "n/rows/cols must be positive");
     if (step < (size_t)cols || out_step < (size_t)cols) return fail(CVS_ERR_INVALID_ARG, "step < cols");
     uint8_t* outs8[3] = {edges, lines_dark, lines_bright};
     const int planes[3] = {CVS_EDGES, CVS_DARK, CVS_BRIGHT};
@@ -714,53 +734,66 @@ extern "C" int cvs_g2_lines_u8_host(cvs_g2* h, const uint8_t* gray, int n, int r
         if (outs8[i]) mask |= CVS_BIT(planes[i]);
     if (!mask) return fail(CVS_ERR_INVALID_ARG, "no output requested");
     CU_TRY(cudaSetDevice(f->device));
-    const size_t pin = align_up((size_t)cols, 128), pf = align_up((size_t)cols * 4, 128), p8 = align_up((size_t)cols, 128);
-    const size_t in_bytes = pin * rows * n, f_bytes = pf * rows * n, o_bytes = p8 * rows * n;
-    // work buffer: [u8 in][3 float maps][3 u8 maps][min/max]
-    CU_TRY(f->work.reserve(in_bytes + 3 * f_bytes + 3 * o_bytes + sizeof(unsigned) * 2 * n + 256));
-    char* w = static_cast<char*>(f->work.p);
-    uint8_t* din = reinterpret_cast<uint8_t*>(w);
-    float* dmap[3];
-    uint8_t* dout[3];
-    for (int i = 0; i < 3; ++i) dmap[i] = reinterpret_cast<float*>(w + in_bytes + i * f_bytes);
-    for (int i = 0; i < 3; ++i) dout[i] = reinterpret_cast<uint8_t*>(w + in_bytes + 3 * f_bytes + i * o_bytes);
-    unsigned* mm = reinterpret_cast<unsigned*>(w + align_up(in_bytes + 3 * f_bytes + 3 * o_bytes, 16));
-    cudaStream_t s = f->stream;
-    cudaMemcpy3DParms cp{};
-    cp.srcPtr = make_cudaPitchedPtr(const_cast<uint8_t*>(gray), step, cols, frame_stride / step);
-    cp.dstPtr = make_cudaPitchedPtr(din, pin, cols, rows);
-    cp.extent = make_cudaExtent(cols, rows, n);
-    cp.kind = cudaMemcpyHostToDevice;
-    if (n == 1 || frame_stride % step == 0) {
-        CU_TRY(cudaMemcpy3DAsync(&cp, s));
-    } else {
-        for (int k = 0; k < n; ++k)
-            CU_TRY(cudaMemcpy2DAsync(din + (size_t)k * pin * rows, pin, gray + (size_t)k * frame_stride, step, cols, rows, cudaMemcpyHostToDevice, s));
-    }
-    BatchGeom g = whole_frame_geom(din, true, n, rows, cols, pin, pin * rows, pf, pf * rows);
-    float* outs[CVS_G2_NPLANES] = {nullptr};
-    for (int i = 0; i < 3; ++i) outs[planes[i]] = dmap[i];
+    const size_t pin = align_up((size_t)cols, 128), pf = align_up((size_t)cols * 4, 128), p8 = pin;
+    // Frames are independent (the min-max normalisation is per frame): process them in chunks round-robin on the handle's
+    // pipeline streams so that upload, kernels and download of neighbouring chunks overlap.
+    const size_t per_frame = pin * rows + 3 * pf * rows + 3 * p8 * rows;  // [u8 in][3 float maps][3 u8 maps]
+    int chunk = (int)std::min<size_t>(16384, std::max<size_t>(1, (256ull << 20) / per_frame));
+    if (chunk > (n + 3) / 4) chunk = std::max(1, (n + 3) / 4);
+    const int NBUF = 3;
+    const int nbuf = std::min(NBUF, (n + chunk - 1) / chunk);
+    const size_t slot_bytes = align_up(per_frame * chunk, 256) + align_up(sizeof(unsigned) * 6 * chunk, 256);
+    CU_TRY(f->work.reserve(slot_bytes * nbuf));
+    cudaStream_t* streams = f->pipe;
+    for (int i = 0; i < nbuf; ++i)
+        if (!streams[i]) CU_TRY(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking));
     SteerSpec st{};
     st.source = CVS_STEER_DOMINANT;
-    int rc = run_fused(f, g, mask, st, outs, s);
-    if (rc) return rc;
-    for (int i = 0; i < 3; ++i) {
-        if (!outs8[i]) continue;
-        CU_TRY(launch_to_u8(dmap[i], pf, pf * rows, n, rows, cols, gain, mm, dout[i], p8, p8 * rows, s));
-        cudaMemcpy3DParms cq{};
-        cq.srcPtr = make_cudaPitchedPtr(dout[i], p8, cols, rows);
-        cq.dstPtr = make_cudaPitchedPtr(outs8[i], out_step, cols, out_frame_stride / out_step);
-        cq.extent = make_cudaExtent(cols, rows, n);
-        cq.kind = cudaMemcpyDeviceToHost;
-        if (n == 1 || out_frame_stride % out_step == 0) {
-            CU_TRY(cudaMemcpy3DAsync(&cq, s));
-        } else {
-            for (int k = 0; k < n; ++k)
-                CU_TRY(cudaMemcpy2DAsync(outs8[i] + (size_t)k * out_frame_stride, out_step, dout[i] + (size_t)k * p8 * rows, p8, cols, rows,
-                                         cudaMemcpyDeviceToHost, s));
+    // strided <-> pitched copies of `nf` frames; one flat copy when both sides are dense (2-D DMA of short rows is slow)
+    auto copy_frames = [&](void* dst, size_t dpitch, size_t dframe, const void* src, size_t spitch, size_t sframe, int nf, cudaMemcpyKind kind,
+                           cudaStream_t s) -> cudaError_t {
+        if (dpitch == spitch && dframe == sframe && dframe == dpitch * rows) return cudaMemcpyAsync(dst, src, dframe * nf, kind, s);
+        if (nf == 1 || (dframe % dpitch == 0 && sframe % spitch == 0)) {
+            cudaMemcpy3DParms cp{};
+            cp.srcPtr = make_cudaPitchedPtr(const_cast<void*>(src), spitch, cols, nf == 1 ? rows : sframe / spitch);
+            cp.dstPtr = make_cudaPitchedPtr(dst, dpitch, cols, nf == 1 ? rows : dframe / dpitch);
+            cp.extent = make_cudaExtent(cols, rows, nf);
+            cp.kind = kind;
+            return cudaMemcpy3DAsync(&cp, s);
+        }
+        for (int k = 0; k < nf; ++k) {
+            cudaError_t e = cudaMemcpy2DAsync(static_cast<char*>(dst) + (size_t)k * dframe, dpitch, static_cast<const char*>(src) + (size_t)k * sframe,
+                                              spitch, cols, rows, kind, s);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    };
+    int ci = 0;
+    for (int f0 = 0; f0 < n; f0 += chunk, ++ci) {
+        const int nf = std::min(chunk, n - f0);
+        cudaStream_t s = streams[ci % nbuf];
+        char* w = static_cast<char*>(f->work.p) + (size_t)(ci % nbuf) * slot_bytes;
+        const size_t in_bytes = pin * rows * chunk, f_bytes = pf * rows * nf, o_bytes = p8 * rows * nf;  // maps: 3*nf dense frames
+        uint8_t* din = reinterpret_cast<uint8_t*>(w);
+        unsigned* mm = reinterpret_cast<unsigned*>(w + align_up(per_frame * chunk, 256));
+        CU_TRY(copy_frames(din, pin, pin * rows, gray + (size_t)f0 * frame_stride, step, frame_stride, nf, cudaMemcpyHostToDevice, s));
+        BatchGeom g = whole_frame_geom(din, true, nf, rows, cols, pin, pin * rows, pf, pf * rows);
+        float* outs[CVS_G2_NPLANES] = {nullptr};
+        for (int i = 0; i < 3; ++i) outs[planes[i]] = reinterpret_cast<float*>(w + in_bytes + i * f_bytes);
+        int rc = run_fused(f, g, mask, st, outs, s);
+        if (rc) return rc;
+        uint8_t* dout0 = reinterpret_cast<uint8_t*>(w + in_bytes + 3 * f_bytes);
+        const bool all3 = outs8[0] && outs8[1] && outs8[2];
+        if (all3)  // the three maps are 3*nf consecutive frames: one min-max + one conversion launch for all of them
+            CU_TRY(launch_to_u8(outs[planes[0]], pf, pf * rows, 3 * nf, rows, cols, gain, mm, dout0, p8, p8 * rows, s));
+        for (int i = 0; i < 3; ++i) {
+            if (!outs8[i]) continue;
+            uint8_t* dout = dout0 + i * o_bytes;
+            if (!all3) CU_TRY(launch_to_u8(outs[planes[i]], pf, pf * rows, nf, rows, cols, gain, mm + 2 * (size_t)i * nf, dout, p8, p8 * rows, s));
+            CU_TRY(copy_frames(outs8[i] + (size_t)f0 * out_frame_stride, out_step, out_frame_stride, dout, p8, p8 * rows, nf, cudaMemcpyDeviceToHost, s));
         }
     }
-    CU_TRY(cudaStreamSynchronize(s));
+    for (int i = 0; i < nbuf; ++i) CU_TRY(cudaStreamSynchronize(streams[i]));
     return CVS_OK;
 }
 

@@ -205,6 +205,11 @@ CVS_API int cvs_pyr_down_dev(int device, const cvs_batch* b, float* out, void* s
 CVS_API int cvs_g2_run_batch_host(cvs_g2* h, const float* in, int n, int rows, int cols, size_t in_step,
                                   size_t in_frame_stride, unsigned mask, float* const* outs,
                                   size_t out_step, size_t out_frame_stride);
+/* G4/H4 twin (config 4 with frames in host memory).  steer_source: CVS_STEER_DOMINANT (the G4 theta_d of this
+ * library's extension) or CVS_STEER_SCALAR with theta_scalar; a host theta map is not taken here. */
+CVS_API int cvs_g4_run_batch_host(cvs_g4* h, const float* in, int n, int rows, int cols, size_t in_step,
+                                  size_t in_frame_stride, unsigned mask, int steer_source, float theta_scalar,
+                                  float* const* outs, size_t out_step, size_t out_frame_stride);
 
 /* ---- the callers' 8-bit post-processing (reference example/steer.cpp:92-104, test/test.cpp:93-95), on the device ----
  * gain > 0: Mat::convertTo(CV_8UC1, gain); gain <= 0: cv::normalize(src, dst, 0, 255, NORM_MINMAX, CV_8UC1), per frame. */

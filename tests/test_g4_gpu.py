@@ -173,3 +173,25 @@ def test_g4_flip_symmetry_and_crop_parity_4k():
     w = o.steer_map_full(th[0, 900:1100, 1500:1800].cpu().numpy())
     assert_close_range(r["g4"][0, 912:1088, 1512:1788].cpu().numpy(), w[0][12:-12, 12:-12], rng, "crop g4")
     assert_close_range(r["magnitude"][0, 912:1088, 1512:1788].cpu().numpy(), w[2][12:-12, 12:-12], rng, "crop magnitude")
+
+
+def test_g4_host_batch_api_matches_device_path():
+    """cvs_g4_run_batch_host: chunked H2D / kernel / D2H pipeline == one device launch (scalar angle and theta_d)."""
+    fr = np.stack([synth(4700 + i, 110, 190) for i in range(6)])
+    g = G4Batch()
+    for theta, steer in ((0.45, capi.STEER_SCALAR), (None, capi.STEER_DOMINANT)):
+        mask = capi.G4_MASK_STEER | (capi.bit(capi.G4_THETA) | capi.bit(capi.G4_STRENGTH) if theta is None else 0)
+        dev = g.run(torch.from_numpy(fr).cuda(), mask, steer=steer, theta=theta or 0.0)
+        planes = [p for p in range(capi.G4_NPLANES) if mask >> p & 1]
+        oh = {p: torch.empty((6, 110, 190), dtype=torch.float32).pin_memory() for p in planes}
+        g.run_host(torch.from_numpy(fr).pin_memory(), mask, oh, theta=theta)
+        for p in planes:
+            assert torch.equal(oh[p], dev[capi.G4_PLANE_NAMES[p]].cpu()), capi.G4_PLANE_NAMES[p]
+    w = ref.SteerableFiltersG4(fr[2]).steer_scalar(0.45)          # and the oracle, on one frame
+    oh = {capi.G4T: torch.empty((6, 110, 190), dtype=torch.float32)}
+    g.run_host(torch.from_numpy(fr), capi.bit(capi.G4T), oh, theta=0.45)
+    assert_close_range(oh[capi.G4T][2].numpy(), w[0], 1000.0, "g4 host scalar")
+    with pytest.raises(capi.CvsError):                             # a G2 handle is refused
+        from cvsteer_b200.batch import G2Batch
+        g2 = G2Batch()
+        capi.check(capi.lib().cvs_g4_run_batch_host(g2._h, 0, 1, 1, 1, 4, 4, 1, 0, 0.0, None, 4, 4))
