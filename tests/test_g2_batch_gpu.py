@@ -439,3 +439,56 @@ def test_fuzz_shapes_masks_vs_oracle():
                     assert_close_range(r[k][i].cpu().numpy(), w[j], s, tag + k)
             if "phase" in r:
                 assert_angle_close(r["phase"][i].cpu().numpy(), w[4], w[3], 2 * np.pi, tag + "phase")
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_sweep_vs_oracle(seed):
+    """Seeded sweep over what a caller can vary at once: frame size (incl. smaller than the filter and not a multiple of the
+    tile), batch size, 8-bit or float input, a padded / misaligned input view, and a random plane mask."""
+    r = np.random.default_rng(9000 + seed)
+    rows = int(r.choice([r.integers(1, 12), r.integers(12, 140), r.integers(140, 330)]))
+    cols = int(r.choice([r.integers(1, 12), r.integers(12, 140), r.integers(140, 420)]))
+    n = int(r.integers(1, 4))
+    u8 = bool(r.integers(0, 2))
+    if u8:
+        fr = r.integers(0, 256, (n, rows, cols), dtype=np.uint8)
+    else:
+        fr = r.uniform(0, 255, (n, rows, cols)).astype(np.float32)
+    x = torch.from_numpy(fr).cuda()
+    if r.integers(0, 2):                                   # non-dense view: odd column offset and a longer pitch
+        off, extra = int(r.integers(0, 4)), int(r.integers(0, 9))
+        buf = torch.zeros((n, rows + 2, cols + off + extra), dtype=x.dtype, device="cuda")
+        buf[:, 1:rows + 1, off:off + cols] = x
+        x = buf[:, 1:rows + 1, off:off + cols]
+    mask = int(r.integers(1, 1 << capi.G2_NPLANES))
+    if r.integers(0, 3) == 0:
+        mask = int(r.choice([capi.G2_MASK_STATE, capi.G2_MASK_ORIENT, capi.G2_MASK_FULL]))
+    g = G2Batch()
+    res = g.run(x, mask)
+    full = g.run(x, (1 << capi.G2_NPLANES) - 1)              # every plane, same launch geometry
+    names = [capi.G2_PLANE_NAMES[p] for p in range(capi.G2_NPLANES) if mask >> p & 1]
+    assert sorted(res) == sorted(names)
+    for k in names:                                        # a mask selects planes, it never changes their values...
+        a, b = res[k], full[k]
+        if k in ("g2", "h2", "e", "magnitude", "phase", "edges", "lines_dark", "lines_bright", "theta", "strength") and \
+                mask in (capi.G2_MASK_STATE, capi.G2_MASK_ORIENT, capi.G2_MASK_FULL):
+            continue                                       # ...except that the static fast-math masks round differently
+        assert torch.equal(a, b), (k, hex(mask))
+    for i in range(n):                                     # and the values are the oracle's
+        o = ref.SteerableFiltersG2(fr[i].astype(np.float32))
+        rng = max(basis_range([getattr(o, k) for k in STATE]), 1e-3)
+        for k in STATE:
+            if k in res:
+                assert_close_range(res[k][i].cpu().numpy(), getattr(o, k), rng, f"{k} seed{seed}")
+        for k in ("c1", "c2", "c3", "strength"):
+            if k in res:
+                assert_close_range(res[k][i].cpu().numpy(), getattr(o, k), rng * rng, f"{k} seed{seed}")
+        if "theta" in res:
+            assert_angle_close(res["theta"][i].cpu().numpy(), o.theta, o.strength, np.pi, f"theta seed{seed}")
+        th = full["theta"][i].cpu().numpy()
+        w = o.steer_map_full(th)
+        for k, j, s in (("g2", 0, rng), ("h2", 1, rng), ("e", 2, rng * rng), ("magnitude", 3, rng)):
+            if k in res:
+                assert_close_range(res[k][i].cpu().numpy(), w[j], s, f"{k} seed{seed}")
+        if "phase" in res:
+            assert_angle_close(res["phase"][i].cpu().numpy(), w[4], w[3], 2 * np.pi, f"phase seed{seed}")

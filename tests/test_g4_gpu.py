@@ -195,3 +195,41 @@ def test_g4_host_batch_api_matches_device_path():
         from cvsteer_b200.batch import G2Batch
         g2 = G2Batch()
         capi.check(capi.lib().cvs_g4_run_batch_host(g2._h, 0, 1, 1, 1, 4, 4, 1, 0, 0.0, None, 4, 4))
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_g4_random_sweep_vs_oracle(seed):
+    """Seeded sweep: frame size (down to smaller than the 13-tap filter), batch size, 8-bit / float input, padded views,
+    random plane masks, steering from a random per-pixel angle map."""
+    r = np.random.default_rng(9500 + seed)
+    rows = int(r.choice([r.integers(1, 16), r.integers(16, 140), r.integers(140, 300)]))
+    cols = int(r.choice([r.integers(1, 16), r.integers(16, 140), r.integers(140, 400)]))
+    n = int(r.integers(1, 4))
+    u8 = bool(r.integers(0, 2))
+    fr = r.integers(0, 256, (n, rows, cols), dtype=np.uint8) if u8 else r.uniform(0, 255, (n, rows, cols)).astype(np.float32)
+    x = torch.from_numpy(fr).cuda()
+    if r.integers(0, 2):
+        off, extra = int(r.integers(0, 4)), int(r.integers(0, 9))
+        buf = torch.zeros((n, rows + 1, cols + off + extra), dtype=x.dtype, device="cuda")
+        buf[:, :rows, off:off + cols] = x
+        x = buf[:, :rows, off:off + cols]
+    th = r.uniform(-4, 4, (n, rows, cols)).astype(np.float32)
+    steerable = (1 << capi.G4_THETA) - 1                    # basis + g4 / h4 / magnitude / phase
+    mask = int(r.integers(1, steerable + 1))
+    if r.integers(0, 3) == 0:
+        mask = int(r.choice([capi.G4_MASK_BASIS, capi.G4_MASK_STEER]))
+    g = G4Batch()
+    res = g.run(x, mask, steer=capi.STEER_MAP, theta_map=torch.from_numpy(th).cuda())
+    assert sorted(res) == sorted(capi.G4_PLANE_NAMES[p] for p in range(capi.G4_NPLANES) if mask >> p & 1)
+    for i in range(n):
+        o = ref.SteerableFiltersG4(fr[i].astype(np.float32))
+        rng = max(basis_range([getattr(o, k) for k in P]), 1e-3)
+        for k in P:
+            if k in res:
+                assert_close_range(res[k][i].cpu().numpy(), getattr(o, k), rng, f"{k} seed{seed}")
+        w = o.steer_map_full(th[i])
+        for k, j in (("g4", 0), ("h4", 1), ("magnitude", 2)):
+            if k in res:
+                assert_close_range(res[k][i].cpu().numpy(), w[j], rng, f"{k} seed{seed}")
+        if "phase" in res:
+            assert_angle_close(res["phase"][i].cpu().numpy(), w[3], w[2], 2 * np.pi, f"phase seed{seed}")
