@@ -17,6 +17,8 @@ ONE JSON line.  See DESIGN.md "Measurement" for how every field is derived.
              frame-parallel like the reference's cv::parallel_for_ (example/steer.cpp:169), bounded sample
 
 --impl reference runs only that CPU path and prints the same line shape with "impl": "reference".
+--cfg1 measures BASELINE.json configs[0] instead (the cvsteer-run per-file body on the bundled test image: one-file
+latency and file-batch throughput through cvs_g2_lines_u8_host, with the oracle on one host core beside them).
 """
 import argparse
 import json
@@ -331,6 +333,56 @@ def run_ours(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def cfg1_line(device=0):
+    """configs[0]: host-timed (the call synchronises): 8-bit gray in host memory -> three 8-bit maps in host memory."""
+    import ctypes as C
+
+    import numpy as np
+    import torch
+    from cvsteer_b200 import capi
+    root = os.path.dirname(os.path.abspath(__file__))
+    fish = np.load(os.path.join(root, "tests", "golden", "fish_fixture.npz"))["fish"]
+    rows, cols = fish.shape
+    lib = capi.lib()
+    h = C.c_void_p()
+    capi.check(lib.cvs_g2_create(C.byref(h), device, 4, 0.67))
+
+    def run(batch, outs):
+        n = batch.shape[0]
+        capi.check(lib.cvs_g2_lines_u8_host(h, batch.data_ptr(), n, rows, cols, cols, rows * cols, 0.0, outs[0].data_ptr(),
+                                            outs[1].data_ptr(), outs[2].data_ptr(), cols, rows * cols))
+
+    res = {}
+    for n, reps in ((1, 200), (2048, 10)):
+        batch = torch.from_numpy(np.repeat(fish[None], n, axis=0)).pin_memory()
+        outs = [torch.empty_like(batch).pin_memory() for _ in range(3)]
+        for _ in range(3):
+            run(batch, outs)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            run(batch, outs)
+        res[n] = (time.perf_counter() - t0) / reps
+    from oracle import cvsteer_ref as ref          # CPU leg (cpu_baseline): the oracle, timed beside the GPU path
+    import cv2
+    cv2.setNumThreads(1)
+
+    def cpu_one():
+        _, (g2, h2, e, mag, ph) = ref.g2_full(fish)
+        return [ref.normalize_minmax_u8(m) for m in (ref.find_edges(mag, ph), ref.find_dark_lines(mag, ph), ref.find_bright_lines(mag, ph))]
+    cpu_one()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        cpu_one()
+    t_cpu = (time.perf_counter() - t0) / 20
+    lib.cvs_g2_destroy(h)
+    px = rows * cols
+    return {"config": "cfg1", "what": "cvsteer-run per-file body (gray u8 -> edges / dark lines / bright lines u8) on the bundled %dx%d image" % (cols, rows),
+            "n_gpus": 1, "one_file_ms": round(res[1] * 1e3, 4), "one_file_Mpix_s": round(px / 1e6 / res[1], 1),
+            "batch_2048_files_ms": round(res[2048] * 1e3, 3), "batch_Mpix_s": round(2048 * px / 1e6 / res[2048], 1),
+            "batch_files_per_s": round(2048 / res[2048], 0), "timing": "host wall clock around the synchronous C-ABI call, pinned host buffers",
+            "cpu_oracle_one_core_ms": round(t_cpu * 1e3, 3), "cpu_oracle_Mpix_s": round(px / 1e6 / t_cpu, 1)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -342,8 +394,13 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--quick", action="store_true", help="skip the other-modes table")
+    ap.add_argument("--cfg1", action="store_true", help="configs[0] instead: cvsteer-run per-file body on the bundled test image")
     args = ap.parse_args()
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
+    if args.cfg1:
+        if rank == 0:
+            print(json.dumps(cfg1_line(local_rank)), flush=True)
+        return
     if args.impl == "reference":
         run_reference(args, rank, world)
         return

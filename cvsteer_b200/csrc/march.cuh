@@ -236,18 +236,42 @@ __device__ __forceinline__ void patch_reflect(float* tile, int x0, int ytop, int
 }
 
 // Cooperative reflect-indexed load: any size (iterated folding), any alignment, fp32 or u8 input.
+// Row-oriented: a thread owns tile columns t and t + nthreads for every tile row, so the column fold is done once per
+// thread and a warp's load is one contiguous 128-byte (32-byte for u8) segment; the row fold is warp-uniform and a
+// single select unless the image is shorter than the tile, so the row loop is unrolled to keep 8 loads in flight.
 template <int R, int TWH, int TROWS, typename TIn>
 __device__ __forceinline__ void load_tile_manual(float* tile, const MarchArgs& a, int frame, int x0, int ytop,
                                                  int nthreads)
 {
     const char* base = (const char*)a.in + (long long)frame * a.in_frame_stride;
-    for (int i = threadIdx.x; i < TROWS * TWH; i += nthreads) {
-        const int rt = i / TWH, ct = i % TWH;
-        const int gy = dev::reflect101(ytop + rt, a.full_rows) - a.y_origin;
-        const int gx = dev::reflect101(x0 - march_halo_left(R) + ct, a.cols);
-        float v = 0.f;
-        if (gy >= 0 && gy < a.buf_rows) v = (float)((const TIn*)(base + (long long)gy * a.in_pitch))[gx];
-        tile[i] = v;
+    const int c0 = threadIdx.x, c1 = threadIdx.x + nthreads;  // TWH <= 2 * nthreads
+    const bool two = c1 < TWH;
+    const int gx0 = dev::reflect101(x0 - march_halo_left(R) + c0, a.cols);
+    const int gx1 = two ? dev::reflect101(x0 - march_halo_left(R) + c1, a.cols) : gx0;
+    const int n = a.full_rows;
+    if (ytop >= -(n - 1) && ytop + TROWS - 1 <= 2 * (n - 1)) {
+        // one fold reaches every row of this tile (always, unless the image is shorter than the tile): branch-free rows
+#pragma unroll 8
+        for (int rt = 0; rt < TROWS; ++rt) {
+            const int p = ytop + rt;
+            const int gy = (p < 0 ? -p : (p >= n ? 2 * (n - 1) - p : p)) - a.y_origin;
+            const bool ok = gy >= 0 && gy < a.buf_rows;  // band mode: rows outside the resident band are never used
+            const TIn* rp = (const TIn*)(base + (long long)(ok ? gy : 0) * a.in_pitch);
+            const float v0 = (float)rp[gx0], v1 = (float)rp[gx1];
+            tile[rt * TWH + c0] = ok ? v0 : 0.f;
+            if (two) tile[rt * TWH + c1] = ok ? v1 : 0.f;
+        }
+    } else {
+        for (int rt = 0; rt < TROWS; ++rt) {
+            const int gy = dev::reflect101(ytop + rt, n) - a.y_origin;
+            float v0 = 0.f, v1 = 0.f;
+            if (gy >= 0 && gy < a.buf_rows) {
+                const TIn* rp = (const TIn*)(base + (long long)gy * a.in_pitch);
+                v0 = (float)rp[gx0], v1 = (float)rp[gx1];
+            }
+            tile[rt * TWH + c0] = v0;
+            if (two) tile[rt * TWH + c1] = v1;
+        }
     }
     __syncthreads();
 }

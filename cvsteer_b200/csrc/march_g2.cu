@@ -3,6 +3,10 @@
 
 namespace cvs {
 
+// march_g2_lines.cu (its own translation unit so that `make -j` compiles it in parallel)
+cudaError_t launch_march_g2_lines(const BatchGeom& g, const MarchArgs& a, const TapTable<G2Fam::NSETS, G2Fam::R>& tt, dim3 grid, cudaStream_t stream,
+                                  LaunchInfo* info);
+
 cudaError_t launch_march_g2(const FamilyTaps& taps, const BatchGeom& g, const MarchArgs& a, bool dom, cudaStream_t stream, LaunchInfo* info)
 {
     TapTable<G2Fam::NSETS, G2Fam::R> tt;
@@ -13,6 +17,8 @@ cudaError_t launch_march_g2(const FamilyTaps& taps, const BatchGeom& g, const Ma
     if (dom && mask == CVS_G2_MASK_ORIENT) return launch_march_mask<G2Fam, CVS_G2_MASK_ORIENT, true>(g, a, tt, grid, stream, info, "g2_march<M1>");
     if (dom && mask == CVS_G2_MASK_FULL) return launch_march_mask<G2Fam, CVS_G2_MASK_FULL, true>(g, a, tt, grid, stream, info, "g2_march<M2>");
     if (dom && mask == CVS_G2_MASK_STATE) return launch_march_mask<G2Fam, CVS_G2_MASK_STATE, true>(g, a, tt, grid, stream, info, "g2_march<M0>");
+    static const bool no_lines = getenv("CVS_NO_STATIC_LINES") != nullptr;  // A/B switch
+    if (dom && mask == CVS_G2_MASK_LINES && !no_lines) return launch_march_g2_lines(g, a, tt, grid, stream, info);
     return launch_march_mask<G2Fam, 0u>(g, a, tt, grid, stream, info, "g2_march<dyn>");
 }
 

@@ -67,6 +67,8 @@ typedef enum cvs_g2_plane {
 #define CVS_G2_MASK_ORIENT (CVS_BIT(CVS_THETA) | CVS_BIT(CVS_STRENGTH) | CVS_BIT(CVS_E))
 /* M2: full fused basis+steer+orientation: theta_d, strength, g2, h2, e, magnitude, phase */
 #define CVS_G2_MASK_FULL (CVS_G2_MASK_ORIENT | CVS_BIT(CVS_G2T) | CVS_BIT(CVS_H2T) | CVS_BIT(CVS_MAG) | CVS_BIT(CVS_PHASE))
+/* the cvsteer-run per-file outputs (example/steer.cpp:88-90): findEdges / findDarkLines / findBrightLines at theta_d */
+#define CVS_G2_MASK_LINES (CVS_BIT(CVS_EDGES) | CVS_BIT(CVS_DARK) | CVS_BIT(CVS_BRIGHT))
 
 typedef enum cvs_g4_plane {
     CVS_G4A = 0, CVS_G4B, CVS_G4C, CVS_G4D, CVS_G4E,                /* G4.cpp:69-73 */

@@ -1,7 +1,5 @@
-"""Secondary workloads of BASELINE.json (configs[0], configs[2..4]); the contract bench (bench.py) covers configs[1].
-
-  cfg1  the cvsteer-run per-file body on the bundled 256x185 test image: latency of ONE file through the C ABI
-        (cvs_g2_lines_u8_host, n=1), throughput of a 2048-file batch, and the cv2 oracle on one host core beside them
+"""Secondary workloads of BASELINE.json (configs[2..4]); the contract bench (bench.py) covers configs[1], and
+`python bench.py --cfg1` configs[0] (the cvsteer-run per-file body with its CPU leg).
 
   cfg3  G2/H2 orientation (M1) over a 5-level pyramid, 3840x2160 frames, batch 256 TOTAL, sharded by frame (strong scaling)
   cfg4  G4/H4 steer at a per-pixel theta map + magnitude + phase, 3840x2160, batch 256 total, sharded by frame
@@ -41,54 +39,6 @@ def timed(fn, warm, steps, world, dev):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     return ms
-
-
-def cfg1(device):
-    """configs[0]: host-timed (the call synchronises): 8-bit gray in host memory -> three 8-bit maps in host memory."""
-    import ctypes as C
-
-    import numpy as np
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    fish = np.load(os.path.join(root, "tests", "golden", "fish_fixture.npz"))["fish"]
-    rows, cols = fish.shape
-    lib = capi.lib()
-    h = C.c_void_p()
-    capi.check(lib.cvs_g2_create(C.byref(h), device, 4, 0.67))
-
-    def run(batch, outs):
-        n = batch.shape[0]
-        capi.check(lib.cvs_g2_lines_u8_host(h, batch.data_ptr(), n, rows, cols, cols, rows * cols, 0.0, outs[0].data_ptr(),
-                                            outs[1].data_ptr(), outs[2].data_ptr(), cols, rows * cols))
-
-    res = {}
-    for n, reps in ((1, 200), (2048, 10)):
-        batch = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(fish, (n, rows, cols)))).pin_memory()
-        outs = [torch.empty_like(batch).pin_memory() for _ in range(3)]
-        for _ in range(3):
-            run(batch, outs)
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            run(batch, outs)
-        res[n] = (time.perf_counter() - t0) / reps
-    from oracle import cvsteer_ref as ref          # the CPU leg of a bench: the one place tools may time the oracle
-    import cv2
-    cv2.setNumThreads(1)
-
-    def cpu_one():
-        _, (g2, h2, e, mag, ph) = ref.g2_full(fish)
-        return [ref.normalize_minmax_u8(m) for m in (ref.find_edges(mag, ph), ref.find_dark_lines(mag, ph), ref.find_bright_lines(mag, ph))]
-    cpu_one()
-    t0 = time.perf_counter()
-    for _ in range(20):
-        cpu_one()
-    t_cpu = (time.perf_counter() - t0) / 20
-    lib.cvs_g2_destroy(h)
-    px = rows * cols
-    return {"config": "cfg1", "what": "cvsteer-run per-file body (gray u8 -> edges / dark lines / bright lines u8) on the bundled %dx%d image" % (cols, rows),
-            "n_gpus": 1, "one_file_ms": round(res[1] * 1e3, 4), "one_file_Mpix_s": round(px / 1e6 / res[1], 1),
-            "batch_2048_files_ms": round(res[2048] * 1e3, 3), "batch_Mpix_s": round(2048 * px / 1e6 / res[2048], 1),
-            "batch_files_per_s": round(2048 / res[2048], 0), "timing": "host wall clock around the synchronous C-ABI call, pinned host buffers",
-            "cpu_oracle_one_core_ms": round(t_cpu * 1e3, 3), "cpu_oracle_Mpix_s": round(px / 1e6 / t_cpu, 1)}
 
 
 def main():
@@ -141,10 +91,6 @@ def main():
                     "algorithmic_GB_s": round(px0 * 24 / 1e9 / (ms / 1e3), 1),
                     "algorithmic_Tinstr_s": round(px0 * 323 / 1e12 / (ms / 1e3), 2), "kernel": g4.last_launch()["kernel"]}
             del x, th, outs
-        elif cfg == "cfg1":
-            if rank == 0:
-                print(json.dumps(cfg1(local)), flush=True)
-            continue
         elif cfg == "cfg5":
             H = W = a.big
             process, down, _ = multi.cuda_callables(capi.G2_MASK_ORIENT)

@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--g4", action="store_true")
     ap.add_argument("--ffma", action="store_true")
     ap.add_argument("--only-g4", action="store_true")
+    ap.add_argument("--lines", action="store_true", help="only the cvsteer-run mask (edges / dark / bright), float and 8-bit input")
     a = ap.parse_args()
     out = {}
     if a.ffma:
@@ -41,6 +42,13 @@ def main():
     x = torch.rand((a.n, a.rows, a.cols), device="cuda") * 255
     mpix = a.n * a.rows * a.cols / 1e6
     g = G2Batch()
+    if a.lines:
+        outs = {p: torch.empty((a.n, a.rows, a.cols), device="cuda") for p in (capi.EDGES, capi.DARK, capi.BRIGHT)}
+        for name, xin, bpp in (("lines_f32", x, 16), ("lines_u8", x.to(torch.uint8), 13)):
+            ms = time_ms(lambda: g.run(xin, capi.G2_MASK_LINES, outs=outs))
+            out[name] = {"ms": round(ms, 4), "Gpix_s": round(mpix / ms, 2), "GB_s": round(mpix * bpp / ms, 1), "k": g.last_launch()["kernel"]}
+        print(json.dumps(out))
+        return
     for name, mask, bpp in (() if a.only_g4 else (("M0", capi.G2_MASK_STATE, 52), ("M1", capi.G2_MASK_ORIENT, 16), ("M2", capi.G2_MASK_FULL, 32))):
         outs = {p: torch.empty((a.n, a.rows, a.cols), device="cuda") for p in range(capi.G2_NPLANES) if mask >> p & 1}
         ms = time_ms(lambda: g.run(x, mask, outs=outs))
