@@ -7,5 +7,5 @@ FL="-std=c++20 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo --expt-rela
 nvcc $FL "$@" -c march_g2.cu -o build/var_$name/march_g2.o &
 nvcc $FL "$@" -c march_g4.cu -o build/var_$name/march_g4.o &
 wait
-nvcc -shared -gencode arch=compute_100a,code=sm_100a -cudart static -o ../libcvsteer_b200_$name.so build/capi.o build/kernels.o build/taps.o build/var_$name/march_g2.o build/var_$name/march_g4.o
+nvcc -shared -gencode arch=compute_100a,code=sm_100a -cudart static -o ../libcvsteer_b200_$name.so build/capi.o build/kernels.o build/taps.o build/var_$name/march_g2.o build/var_$name/march_g4.o build/march_g2_lines.o
 echo built $name

@@ -33,6 +33,13 @@
 // 1: the slot dispatch of the rolled loop is a balanced compare tree instead of a switch (which nvcc lowers to a
 // constant-memory jump table: LDC + BRX on the critical path of every row).
 // masks with at most this many planes keep a 64-bit base per plane in registers (2 registers each)
+// Two pixels per thread for the issue-bound static masks (see k_march's PX).  Off by default: 198 instead of 217
+// instructions per pixel-row, but the K-fold unrolled body grows to 57 KB and falls out of the instruction cache
+// (M2 138.9 -> 118.6, M1 194 -> 138 Gpix/s); with the rolled loop it does win (M2 130.9 -> 135.6, M1 172 -> 178) but stays
+// below the unrolled one-pixel kernel.  Kept for builds that trade the unrolled body away (build_variant.sh).
+#ifndef CVS_MARCH_PX2
+#define CVS_MARCH_PX2 0
+#endif
 #ifndef CVS_CURSOR_MAX_PLANES
 #define CVS_CURSOR_MAX_PLANES 8
 #endif
@@ -153,6 +160,7 @@ struct OutCursor {
     unsigned long long th_base;  // steering-angle map (same layout as the outputs); dead unless theta() is used
     unsigned idx;                // element index of this thread's pixel relative to the bases
     unsigned pitch_elems;
+    mutable float pend[NPLANES];  // two-pixel threads: the left pixel's value waits here for its neighbour (registers)
     __device__ __forceinline__ OutCursor(const MarchArgs& a, long long band_off, int x)
     {
 #pragma unroll
@@ -167,6 +175,13 @@ struct OutCursor {
     __device__ __forceinline__ void put(const MarchArgs&, int q, float v) const
     {
         asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %1, 4, %0;\n\tst.global.cs.f32 [a], %2;\n\t}" ::"l"(base[q]), "r"(idx), "f"(v) : "memory");
+    }
+    // two adjacent pixels of one thread as one 8-byte store (x even, bases and pitch multiples of 8: host-checked)
+    __device__ __forceinline__ void put2(const MarchArgs&, int q, float v0, float v1) const
+    {
+        asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %1, 4, %0;\n\tst.global.cs.v2.f32 [a], {%2, %3};\n\t}" ::"l"(base[q]), "r"(idx), "f"(v0),
+                     "f"(v1)
+                     : "memory");
     }
     // steering angle of this thread's pixel `rows_ahead` output rows below the current one
     __device__ __forceinline__ float theta(const MarchArgs&, int rows_ahead = 0) const
@@ -183,16 +198,34 @@ struct OutCursor {
 template <int NPLANES>
 struct OutCursor<0u, NPLANES> {  // run-time mask: one shared byte offset, 64-bit add per plane at the store
     long long off, pitch;
+    mutable float pend[NPLANES];
     __device__ __forceinline__ OutCursor(const MarchArgs& a, long long band_off, int x) : off(band_off + 4ll * x), pitch(a.out_pitch) {}
     __device__ __forceinline__ void put(const MarchArgs& a, int q, float v) const
     {
         __stcs(reinterpret_cast<float*>(reinterpret_cast<char*>(a.out[q]) + off), v);
+    }
+    __device__ __forceinline__ void put2(const MarchArgs& a, int q, float v0, float v1) const
+    {
+        __stcs(reinterpret_cast<float2*>(reinterpret_cast<char*>(a.out[q]) + off), make_float2(v0, v1));
     }
     __device__ __forceinline__ float theta(const MarchArgs& a, int rows_ahead = 0) const
     {
         return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(a.theta_map) + off + rows_ahead * pitch);
     }
     __device__ __forceinline__ void next_row() { off += pitch; }
+};
+
+// Views of a cursor for threads that own two adjacent pixels: the epilogue of the left pixel parks its values, the
+// epilogue of the right pixel stores both as one 8-byte access per plane.
+template <class Cur>
+struct PairLeft {
+    const Cur& c;
+    __device__ __forceinline__ void put(const MarchArgs&, int q, float v) const { c.pend[q] = v; }
+};
+template <class Cur>
+struct PairRight {
+    const Cur& c;
+    __device__ __forceinline__ void put(const MarchArgs& a, int q, float v) const { c.put2(a, q, c.pend[q], v); }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -288,9 +321,10 @@ __device__ __forceinline__ void load_tile_manual(float* tile, const MarchArgs& a
 // this costs shared-memory reads and ~4 % more arithmetic instead of a second pass over the input in HBM.
 // CTA region: output rows [yb/2, ceil((yb+nrows)/2)) x output columns [x0/2, x0/2 + 64); thread t takes column t & 63 and
 // the first / second half of the rows (t >> 6), marching with a 5-row window of horizontal sums.
-template <int R, int BH>
+template <int R, int BH, int NT>
 __device__ __forceinline__ void emit_next_level(const float* tile, const MarchArgs& a, int frame, int x0, int yb)
 {
+    static_assert(NT == 64 || NT == 128, "64 output columns x 1 or 2 row halves");
     constexpr int TWH = march_tile_width(R), HL = march_halo_left(R);
     int nrows = a.out_row_end - yb;
     nrows = nrows < BH ? nrows : BH;
@@ -298,7 +332,7 @@ __device__ __forceinline__ void emit_next_level(const float* tile, const MarchAr
     const int xl = threadIdx.x & 63, half = threadIdx.x >> 6;
     const int xo = (x0 >> 1) + xl;
     const int nout = (nrows + 1) >> 1;                 // output rows of this CTA (yb is even)
-    const int per = (nout + 1) >> 1;
+    const int per = NT == 128 ? (nout + 1) >> 1 : nout;
     const int ly0 = half * per, ly1 = min(nout, ly0 + per);
     if (xo >= ocols || ly0 >= ly1) return;
     const float* tc = tile + 2 * xl + HL;              // tile column of input column 2*xo
@@ -320,14 +354,19 @@ __device__ __forceinline__ void emit_next_level(const float* tile, const MarchAr
     }
 }
 
-template <class Fam, unsigned MASK /* 0 = use a.mask at run time */, bool USE_TMA, typename TIn, bool BAKED>
-__global__ void __launch_bounds__(MARCH_TW, Fam::MIN_CTAS)
+// PX = pixels (adjacent columns) per thread.  PX = 2 halves the per-pixel cost of everything that is per THREAD and row:
+// shared-memory loads (K + 1 values as 8-byte loads feed two pixels instead of K values feeding one), store instructions
+// and their 64-bit address arithmetic (one 8-byte store per plane for two pixels), loop control.
+template <class Fam, unsigned MASK /* 0 = use a.mask at run time */, bool USE_TMA, typename TIn, bool BAKED, int PX = 1>
+__global__ void __launch_bounds__(MARCH_TW / PX, Fam::MIN_CTAS)
 k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchArgs a,
         const __grid_constant__ TapTable<Fam::NSETS, Fam::R> taps)
 {
     constexpr int R = Fam::R, K = 2 * R + 1, TW = MARCH_TW, TWH = march_tile_width(R), BH = Fam::BH, TROWS = BH + 2 * R;
-    constexpr int NROW = Fam::NROW, NB = Fam::NBASIS;
+    constexpr int NROW = Fam::NROW, NB = Fam::NBASIS, NT = TW / PX;
     static_assert(K <= 13, "extend the slot switch");
+    static_assert(PX == 1 || (PX == 2 && USE_TMA && MASK != 0 && (march_halo_left(R) - R) % 2 == 0),
+                  "two-pixel threads: TMA-staged tile, static mask, 8-byte aligned tap window");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* tile = reinterpret_cast<float*>(smem_raw);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + sizeof(float) * TROWS * TWH);
@@ -349,14 +388,15 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
             ptx::tma_load_3d(tile, &tmap, x0 - march_halo_left(R), ytop - a.y_origin, frame, bar);
         }
         ptx::mbar_wait(bar, 0);
-        patch_reflect<R, TWH, TROWS>(tile, x0, ytop, a.cols, a.full_rows, TW);
+        patch_reflect<R, TWH, TROWS>(tile, x0, ytop, a.cols, a.full_rows, NT);
     } else {
-        load_tile_manual<R, TWH, TROWS, TIn>(tile, a, frame, x0, ytop, TW);
+        load_tile_manual<R, TWH, TROWS, TIn>(tile, a, frame, x0, ytop, NT);
     }
 
     // Threads past the right image edge (ragged last strip) are clamped onto the last valid column: they redo that pixel
     // and store the same value to the same address, so the loop needs no bounds predicate at all.
-    const int x = min(x0 + (int)threadIdx.x, a.cols - 1);
+    // (PX = 2: cols is even, host-checked, so the clamped pair stays aligned)
+    const int x = min(x0 + PX * (int)threadIdx.x, a.cols - PX);
     const float* tcol = tile + (x - x0) + (march_halo_left(R) - R);  // leftmost tap of this thread's column
     int nrows = a.out_row_end - yb;
     nrows = nrows < BH ? nrows : BH;
@@ -368,39 +408,51 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
         else return taps.t[set][i];
     };
 
-    float win[NROW][K];  // (2R+1)-row register window per row-filtered plane; slot indices are compile-time
-    float b[NB];
+    float win[NROW][K][PX];  // (2R+1)-row register window per row-filtered plane; slot indices are compile-time
+    float b[PX][NB];
 
     // One tile row: all unique row passes (even/odd symmetry: R sums + R differences are shared by every filter of the
     // pass), results in r[].
-    float r[NROW];
+    float r[NROW][PX];
     auto row_pass = [&](int rt) {
         const float* src = tcol + rt * TWH;
-        float v[K];
+        float v[K + PX - 1];
+        if constexpr (PX == 2) {  // K + 1 values, 8-byte aligned (x, the halo offset and the tile pitch are even)
+            const float2* src2 = reinterpret_cast<const float2*>(src);
 #pragma unroll
-        for (int k = 0; k < K; ++k) v[k] = src[k];
-        float s[R + 1], d[R + 1];
-        s[0] = v[R];
-        d[0] = 0.f;
+            for (int k = 0; k < (K + 1) / 2; ++k) {
+                const float2 t = src2[k];
+                v[2 * k] = t.x, v[2 * k + 1] = t.y;
+            }
+        } else {
 #pragma unroll
-        for (int i = 1; i <= R; ++i) {
-            s[i] = v[R + i] + v[R - i];
-            d[i] = v[R + i] - v[R - i];
+            for (int k = 0; k < K; ++k) v[k] = src[k];
         }
 #pragma unroll
-        for (int p = 0; p < NROW; ++p) {
-            const int set = Fam::row_set(p);
-            float acc;
-            if (Fam::row_odd(p)) {
-                acc = tap(set, 1) * d[1];
+        for (int px = 0; px < PX; ++px) {
+            float s[R + 1], d[R + 1];
+            s[0] = v[px + R];
+            d[0] = 0.f;
 #pragma unroll
-                for (int i = 2; i <= R; ++i) acc = fmaf(tap(set, i), d[i], acc);
-            } else {
-                acc = tap(set, 0) * s[0];
-#pragma unroll
-                for (int i = 1; i <= R; ++i) acc = fmaf(tap(set, i), s[i], acc);
+            for (int i = 1; i <= R; ++i) {
+                s[i] = v[px + R + i] + v[px + R - i];
+                d[i] = v[px + R + i] - v[px + R - i];
             }
-            r[p] = acc;
+#pragma unroll
+            for (int p = 0; p < NROW; ++p) {
+                const int set = Fam::row_set(p);
+                float acc;
+                if (Fam::row_odd(p)) {
+                    acc = tap(set, 1) * d[1];
+#pragma unroll
+                    for (int i = 2; i <= R; ++i) acc = fmaf(tap(set, i), d[i], acc);
+                } else {
+                    acc = tap(set, 0) * s[0];
+#pragma unroll
+                    for (int i = 1; i <= R; ++i) acc = fmaf(tap(set, i), s[i], acc);
+                }
+                r[p][px] = acc;
+            }
         }
     };
     // Column passes for the window whose NEWEST row is r[] (not yet stored) and whose oldest row still sits in `slot`;
@@ -410,24 +462,29 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
         constexpr int slot = decltype(slot_c)::value;
         if (emit) {  // CTA-uniform: the first 2R rows only feed the window
 #pragma unroll
-            for (int q = 0; q < NB; ++q) {
-                const int rp = Fam::basis_row(q), set = Fam::basis_set(q);
-                auto w = [&](int k) -> float { return k == R ? r[rp] : win[rp][(slot + 1 + R + k + K) % K]; };
-                float acc;
-                if (Fam::basis_odd(q)) {
-                    acc = tap(set, 1) * (w(1) - w(-1));
+            for (int px = 0; px < PX; ++px) {
 #pragma unroll
-                    for (int i = 2; i <= R; ++i) acc = fmaf(tap(set, i), w(i) - w(-i), acc);
-                } else {
-                    acc = tap(set, 0) * w(0);
+                for (int q = 0; q < NB; ++q) {
+                    const int rp = Fam::basis_row(q), set = Fam::basis_set(q);
+                    auto w = [&](int k) -> float { return k == R ? r[rp][px] : win[rp][(slot + 1 + R + k + K) % K][px]; };
+                    float acc;
+                    if (Fam::basis_odd(q)) {
+                        acc = tap(set, 1) * (w(1) - w(-1));
 #pragma unroll
-                    for (int i = 1; i <= R; ++i) acc = fmaf(tap(set, i), w(i) + w(-i), acc);
+                        for (int i = 2; i <= R; ++i) acc = fmaf(tap(set, i), w(i) - w(-i), acc);
+                    } else {
+                        acc = tap(set, 0) * w(0);
+#pragma unroll
+                        for (int i = 1; i <= R; ++i) acc = fmaf(tap(set, i), w(i) + w(-i), acc);
+                    }
+                    b[px][q] = acc;
                 }
-                b[q] = acc;
             }
         }
 #pragma unroll
-        for (int p = 0; p < NROW; ++p) win[p][slot] = r[p];
+        for (int p = 0; p < NROW; ++p)
+#pragma unroll
+            for (int px = 0; px < PX; ++px) win[p][slot][px] = r[p][px];
     };
 
     // The window rotates by one slot per row.  Register files cannot be indexed dynamically, so the slot-dependent code
@@ -437,7 +494,18 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
     // Output addressing: see OutCursor.
     const long long band_off = (long long)frame * a.out_frame_stride + (long long)(yb - a.out_row_origin) * a.out_pitch;
     // per-plane base registers only pay off while there are few planes (2 registers each); wide masks share one offset
-    OutCursor<(__builtin_popcount(MASK) <= CVS_CURSOR_MAX_PLANES ? MASK : 0u), Fam::NPLANES> cur(a, band_off, x);
+    using Cursor = OutCursor<(__builtin_popcount(MASK) <= CVS_CURSOR_MAX_PLANES ? MASK : 0u), Fam::NPLANES>;
+    Cursor cur(a, band_off, x);
+    // point-wise epilogue of the row just finished by col_pass (+ the stores), then on to the next output row
+    auto emit_row = [&](float th) {
+        if constexpr (PX == 1) {
+            Fam::template epilogue<MASK>(b[0], a, cur, th);
+        } else {
+            Fam::template epilogue<MASK>(b[0], a, PairLeft<Cursor>{cur}, th);
+            Fam::template epilogue<MASK>(b[1], a, PairRight<Cursor>{cur}, th);
+        }
+        cur.next_row();
+    };
     int rt_done = 0;  // tile rows already consumed by the unrolled path below (always a multiple of K)
     if constexpr (CVS_MARCH_UNROLL_EPILOGUE && MASK != 0 && !Fam::SHARED_ROW_PASS) {
         // Variant for short epilogues: the whole row body (row pass, column pass, epilogue) is replicated per slot, so the
@@ -456,14 +524,13 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
             float th0 = Fam::template reads_theta_map<MASK>(a) ? cur.theta(a) : 0.f;
             row_pass(2 * R);
             col_pass(true, std::integral_constant<int, 2 * R>{});
-            Fam::template epilogue<MASK>(b, a, cur, th0);
-            cur.next_row();
+            emit_row(th0);
             rt_done = K;
 #pragma unroll 1
             for (; rt_done + K <= total; rt_done += K) {
                 [&]<int... I>(std::integer_sequence<int, I...>) {
                     ((th0 = Fam::template reads_theta_map<MASK>(a) ? cur.theta(a) : 0.f, row_pass(rt_done + I),
-                      col_pass(true, std::integral_constant<int, I>{}), Fam::template epilogue<MASK>(b, a, cur, th0), cur.next_row()),
+                      col_pass(true, std::integral_constant<int, I>{}), emit_row(th0)),
                      ...);
                 }(std::make_integer_sequence<int, K>{});
             }
@@ -501,12 +568,9 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
         }
 #endif
         slot = (slot + 1 == K) ? 0 : slot + 1;
-        if (rt >= 2 * R) {
-            Fam::template epilogue<MASK>(b, a, cur, theta_px);
-            cur.next_row();
-        }
+        if (rt >= 2 * R) emit_row(theta_px);
     }
-    if (a.pyr_out) emit_next_level<R, BH>(tile, a, frame, x0, yb);  // CTA-uniform; the tile is read-only after staging
+    if (a.pyr_out) emit_next_level<R, BH, NT>(tile, a, frame, x0, yb);  // CTA-uniform; the tile is read-only after staging
 }
 
 }  // namespace cvs

@@ -79,13 +79,13 @@ static void fill_tap_table(const FamilyTaps& ft, TapTable<Fam::NSETS, Fam::R>& t
     for (int i = 0; i <= Fam::R; ++i) tt.t[Fam::kScaledSet][i] = scaled[Fam::R + i];
 }
 
-template <class Fam, unsigned MASK, bool TMA, typename TIn, bool BAKED>
+template <class Fam, unsigned MASK, bool TMA, typename TIn, bool BAKED, int PX = 1>
 static cudaError_t launch_march_one(const CUtensorMap& tm, const MarchArgs& a, const TapTable<Fam::NSETS, Fam::R>& tt, dim3 grid,
                                     cudaStream_t stream, LaunchInfo* info, const char* name)
 {
     constexpr int TROWS = Fam::BH + 2 * Fam::R, TWH = march_tile_width(Fam::R);
     constexpr int smem = TROWS * TWH * (int)sizeof(float) + 16;
-    auto kfn = k_march<Fam, MASK, TMA, TIn, BAKED>;
+    auto kfn = k_march<Fam, MASK, TMA, TIn, BAKED, PX>;
     static std::once_flag once;  // one per instantiation
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [&] {
@@ -94,11 +94,11 @@ static cudaError_t launch_march_one(const CUtensorMap& tm, const MarchArgs& a, c
             attr_err = cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     });
     if (attr_err != cudaSuccess) return attr_err;
-    kfn<<<grid, MARCH_TW, smem, stream>>>(tm, a, tt);
+    kfn<<<grid, MARCH_TW / PX, smem, stream>>>(tm, a, tt);
     g_launches.fetch_add(1);
     if (info) {
         info->grid[0] = grid.x, info->grid[1] = grid.y, info->grid[2] = grid.z;
-        info->block = MARCH_TW;
+        info->block = MARCH_TW / PX;
         info->smem = smem;
         snprintf(info->name, sizeof(info->name), "%s", name);
     }
@@ -121,7 +121,19 @@ static bool taps_are_baked(const TapTable<Fam::NSETS, Fam::R>& tt)
 
 // BAKED_OK: whether a baked-tap instantiation exists for this mask (kept to the hot static-mask variants to bound
 // compile time and binary size).
-template <class Fam, unsigned MASK, bool BAKED_OK = false>
+// Two-pixel threads store 8 bytes per plane: every selected plane, the pitch and the frame stride must be multiples of 8
+// and the width even (the clamped last pair stays aligned).
+static inline bool pair_store_ok(const BatchGeom& g, const MarchArgs& a)
+{
+    static const bool disabled = getenv("CVS_PX1") != nullptr;  // A/B switch: one pixel per thread everywhere
+    if (disabled || (g.cols & 1) || (g.out_pitch & 7) || (g.out_frame_stride & 7)) return false;
+    for (int p = 0; p < MARCH_MAX_OUT; ++p)
+        if (a.out[p] && ((uintptr_t)a.out[p] & 7)) return false;
+    return true;
+}
+
+// PX2_OK: whether a two-pixels-per-thread instantiation exists for this mask (issue-bound static masks only).
+template <class Fam, unsigned MASK, bool BAKED_OK = false, bool PX2_OK = false>
 static cudaError_t launch_march_mask(const BatchGeom& g, const MarchArgs& a, const TapTable<Fam::NSETS, Fam::R>& tt, dim3 grid,
                                      cudaStream_t stream, LaunchInfo* info, const char* name)
 {
@@ -132,6 +144,12 @@ static cudaError_t launch_march_mask(const BatchGeom& g, const MarchArgs& a, con
     if (tma_eligible(g, Fam::R) && make_tmap(&tm, g, TWH, TROWS)) {
         if constexpr (BAKED_OK) {
             if (taps_are_baked<Fam>(tt)) {
+                if constexpr (PX2_OK) {
+                    if (pair_store_ok(g, a)) {
+                        snprintf(nm, sizeof(nm), "%s/tma/imm-taps/2px", name);
+                        return launch_march_one<Fam, MASK, true, float, true, 2>(tm, a, tt, grid, stream, info, nm);
+                    }
+                }
                 snprintf(nm, sizeof(nm), "%s/tma/imm-taps", name);
                 return launch_march_one<Fam, MASK, true, float, true>(tm, a, tt, grid, stream, info, nm);
             }
