@@ -52,6 +52,22 @@ extern "C" int cvs_device_count(int* count)
     return CVS_OK;
 }
 
+extern "C" int cvs_enable_peer_access(int device, int peer_device)
+{
+    if (device == peer_device) return CVS_OK;
+    int can = 0;
+    CU_TRY(cudaDeviceCanAccessPeer(&can, device, peer_device));
+    if (!can) return fail(CVS_ERR_CUDA, "device %d has no peer path to device %d", device, peer_device);
+    CU_TRY(cudaSetDevice(device));
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();  // not an error: someone (torch, NCCL, an earlier call) enabled it already
+        return CVS_OK;
+    }
+    CU_TRY(e);
+    return CVS_OK;
+}
+
 extern "C" int cvs_g2_make_taps(int which, int width, float spacing, float* dst)
 {
     if (which < 0 || which >= G2_NUM_TAPSETS || width < 1 || width > MAX_WIDTH || !dst)

@@ -8,6 +8,11 @@
              the only communication is ONE gather of the output bands to a root (NCCL send/recv over NVLink, posted
              as a single batch so all peers stream concurrently).  Results are bit-identical to the whole-image run.
 
+             Alternative to the NCCL gather: `PeerPlanes` maps the root's full-size output planes into every rank
+             (CUDA IPC over NVLink peer memory), and each rank's fused kernel STORES its rows straight into them --
+             compute and gather are one kernel, the transfer overlaps the arithmetic tile by tile, and no staging copy
+             or second pass over the outputs exists on any rank.
+
 The planning functions are pure Python (tested on CPU); `process` callables keep the compute injectable so that the
 world_size-2 gloo tests exercise exactly the code path the NCCL run takes.
 """
@@ -95,9 +100,65 @@ ProcessBand = Callable[[torch.Tensor, int, BandPlan], Dict[str, torch.Tensor]]
 DownBand = Callable[[torch.Tensor, int, BandPlan], torch.Tensor]
 
 
+def plane_layout(names: Sequence[str], rows_per_level: Sequence[int], cols: int) -> Tuple[Dict[Tuple[int, str], Tuple[int, int, int]], int]:
+    """Element offsets of every (level, plane) inside ONE flat fp32 buffer: {(level, name): (offset, rows, cols)}, total.
+    Each plane starts on a 128-byte boundary (32 floats) so that TMA-describable consumers can use it as is."""
+    out, off, c = {}, 0, cols
+    for l, r in enumerate(rows_per_level):
+        for n in names:
+            out[(l, n)] = (off, r, c)
+            off += -(-(r * c) // 32) * 32
+        c = (c + 1) // 2
+    return out, off
+
+
+class PeerPlanes:
+    """Root-owned full-size output planes of a band run, mapped into every rank over CUDA IPC (NVLink peer memory).
+
+    full[level][name] is a [rows_l, cols_l] fp32 tensor on every rank: real memory on `root`, a peer mapping of the
+    same memory elsewhere.  Create once per (image size, plane set) and reuse across steps -- opening IPC handles
+    costs milliseconds.  Ranks must call `fence()` after their kernels before the root reads the planes."""
+
+    def __init__(self, names: Sequence[str], rows: int, cols: int, levels: int, root: int = 0, group=None):
+        from torch.multiprocessing.reductions import reduce_tensor
+        self.root, self.group = root, group
+        rank = dist.get_rank(group)
+        self.names = list(names)
+        self.layout, total = plane_layout(self.names, level_rows(rows, levels), cols)
+        self._flat = None
+        obj = [None]
+        if rank == root:
+            self._flat = torch.empty(total, dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
+            obj = [reduce_tensor(self._flat)]
+        dist.broadcast_object_list(obj, src=root, group=group)
+        if rank != root:
+            rebuild, args = obj[0]
+            here = torch.cuda.current_device()
+            self._flat = rebuild(*args)   # cudaIpcOpenMemHandle inside torch (opened on the OWNER's device index)
+            torch.cuda.set_device(here)
+            # torch maps the block in the owner's context, which does not give THIS rank's GPU access to it: enable the
+            # NVLink peer path explicitly, or the first remote store faults with an illegal address.
+            if self._flat.device.index != here:
+                from . import capi
+                capi.check(capi.lib().cvs_enable_peer_access(here, self._flat.device.index))
+        self.full: List[Dict[str, torch.Tensor]] = [dict() for _ in range(levels)]
+        for (l, n), (off, r, c) in self.layout.items():
+            self.full[l][n] = self._flat[off:off + r * c].view(r, c)
+        dist.barrier(group)               # nobody proceeds (or frees) before every rank holds its mapping
+
+    def rows_of(self, level: int, lo: int, hi: int) -> Dict[str, torch.Tensor]:
+        """Views of rows [lo, hi) of every plane of `level` (contiguous row blocks)."""
+        return {n: t[lo:hi] for n, t in self.full[level].items()}
+
+    def fence(self):
+        """All ranks' stores have landed in the root's memory when this returns on the root."""
+        torch.cuda.current_stream().synchronize()   # kernel completion flushes its peer stores (system-scope release)
+        dist.barrier(self.group)
+
+
 def run_bands(load_rows: Callable[[int, int], torch.Tensor], rows: int, cols: int, levels: int, process: ProcessBand,
-              down: DownBand, root: int = 0, gather: bool = True, radius: int = G2_RADIUS,
-              group=None) -> Tuple[Optional[List[Dict[str, torch.Tensor]]], List[Dict[str, torch.Tensor]], BandPlan]:
+              down: DownBand, root: int = 0, gather=True, radius: int = G2_RADIUS,
+              group=None, peer: Optional[PeerPlanes] = None) -> Tuple[Optional[List[Dict[str, torch.Tensor]]], List[Dict[str, torch.Tensor]], BandPlan]:
     """Row-band pipeline on the calling rank.
 
     load_rows(lo, hi) -> device tensor [hi-lo, cols] with image rows [lo, hi) of level 0 (band + halo).
@@ -105,18 +166,32 @@ def run_bands(load_rows: Callable[[int, int], torch.Tensor], rows: int, cols: in
         rows plan.have[level] of that level.
     down(buf, level, plan) -> tensor holding rows plan.have[level+1] of level+1 (pyr_down in band mode).
     Returns (gathered per-level dicts on root or None, local per-level dicts, plan).
+
+    gather: True / "nccl" -- compute into local planes, then ONE batched NCCL send/recv to the root;
+            "direct"      -- needs `peer` (PeerPlanes): `process(buf, level, plan, outs=...)` writes this rank's rows
+                             straight into the root's planes over NVLink; the only synchronisation is peer.fence();
+            False         -- no gather.
     """
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     plans = plan_bands(rows, world, levels, radius)
     plan = plans[rank]
     local: List[Dict[str, torch.Tensor]] = []
+    direct = gather == "direct"
+    if direct and peer is None:
+        raise ValueError("gather='direct' needs a PeerPlanes")
     if not plan.empty:
         buf = load_rows(*plan.have[0])
         for l in range(levels):
-            local.append(process(buf, l, plan))
+            if direct:
+                local.append(process(buf, l, plan, outs=peer.rows_of(l, *plan.out[l])))
+            else:
+                local.append(process(buf, l, plan))
             if l + 1 < levels:
                 buf = down(buf, l, plan)
+    if direct:
+        peer.fence()
+        return (peer.full if rank == root else None), local, plan
     if not gather or world == 1:
         return (local if rank == root else None), local, plan
     return gather_bands(local, plans, cols, root, group), local, plan
@@ -179,10 +254,15 @@ def cuda_callables(mask: int, width: int = 4, spacing: float = 0.67):
 
     g2 = G2Batch(width, spacing)
 
-    def process(buf: torch.Tensor, level: int, plan: BandPlan):
+    from . import capi
+    ids = {capi.G2_PLANE_NAMES[p]: p for p in range(capi.G2_NPLANES) if mask >> p & 1}
+
+    def process(buf: torch.Tensor, level: int, plan: BandPlan, outs: Optional[Dict[str, torch.Tensor]] = None):
         lo, hi = plan.out[level]
         band = Band(full_rows=plan.rows[level], y_origin=plan.have[level][0], row_begin=lo, row_end=hi)
-        res = g2.run(buf, mask, band=band)
+        if outs is not None:   # caller-owned destinations (possibly peer memory of another GPU): [rows, cols] row blocks
+            outs = {ids[k]: v.unsqueeze(0) for k, v in outs.items()}
+        res = g2.run(buf, mask, band=band, outs=outs)
         return {k: v[0] for k, v in res.items()}
 
     def down(buf: torch.Tensor, level: int, plan: BandPlan):

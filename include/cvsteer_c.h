@@ -102,6 +102,10 @@ typedef struct cvs_g4 cvs_g4;   /* replaces fa::SteerableFiltersG4  (cvsteer/Ste
 CVS_API const char* cvs_version(void);
 CVS_API const char* cvs_last_error(void);     /* thread-local text of the last failure */
 CVS_API int cvs_device_count(int* count);
+/* Let kernels running on `device` load/store memory that lives on `peer_device` (NVLink / NVSwitch peer memory), e.g.
+ * output planes of another GPU mapped through CUDA IPC: the row-band mode then stores each band straight into the root
+ * GPU's planes from inside the fused kernel.  Idempotent; CVS_ERR_CUDA when the two GPUs have no peer path. */
+CVS_API int cvs_enable_peer_access(int device, int peer_device);
 
 /* ---- taps: SteerableFilters::create (cvsteer/SteerableFilters.cpp:33-42) with the reference's tap
  *      functions G21..G23,H21..H24 (G2.cpp:35-42) / G41..G45,H41..H46 (G4.cpp:34-45).  Host-only.

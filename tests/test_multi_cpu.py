@@ -132,3 +132,15 @@ def test_shard_frames():
         flat = [i for lo, hi in got for i in range(lo, hi)]
         assert flat == list(range(n))
         assert max(hi - lo for lo, hi in got) == -(-n // w)
+
+
+def test_plane_layout_for_peer_planes():
+    """Flat buffer behind PeerPlanes: every (level, plane) present once, 128-byte aligned, no overlap, level sizes halve."""
+    names = ["theta", "strength", "e"]
+    rows = multi.level_rows(1001, 5)
+    lay, total = multi.plane_layout(names, rows, 701)
+    assert set(lay) == {(l, n) for l in range(5) for n in names}
+    spans = sorted((off, off + r * c) for off, r, c in lay.values())
+    assert all(off % 32 == 0 for off, _ in spans)
+    assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:])) and spans[-1][1] <= total
+    assert lay[(0, "theta")][1:] == (1001, 701) and lay[(1, "e")][1:] == (501, 351) and lay[(4, "e")][1:] == (63, 44)

@@ -98,8 +98,15 @@ def main():
             band = torch.rand((plan.have[0][1] - plan.have[0][0], W), device=dev) * 255   # this rank's band + halo, resident
             t_c = timed(lambda: multi.run_bands(lambda lo_, hi_: band, H, W, L, process, down, gather=False), 1, a.steps, world, dev)
             t_g = timed(lambda: multi.run_bands(lambda lo_, hi_: band, H, W, L, process, down, gather=True), 1, a.steps, world, dev)
+            t_d = None
+            if world > 1:   # compute and gather fused: each rank's kernels store into the root's planes over NVLink peer memory
+                peer = multi.PeerPlanes(["theta", "strength", "e"], H, W, L)
+                t_d = timed(lambda: multi.run_bands(lambda lo_, hi_: band, H, W, L, process, down, gather="direct", peer=peer), 1, a.steps, world, dev)
+                del peer
             line = {"config": "cfg5", "what": "%dx%d image, G2/H2 M1 + 5-level pyramid, %d row bands + halo" % (H, W, world), "n_gpus": world,
                     "compute_only_ms": round(t_c, 3), "compute_plus_gather_ms": round(t_g, 3),
+                    "fused_peer_store_ms": None if t_d is None else round(t_d, 3),
+                    "Mpix_s_fused_peer_store": None if t_d is None else round(H * W / 1e6 / (t_d / 1e3), 1),
                     "Mpix_s_compute": round(H * W / 1e6 / (t_c / 1e3), 1), "Mpix_s_with_gather": round(H * W / 1e6 / (t_g / 1e3), 1),
                     "gather_bytes_to_root": int(3 * 4 * 1.332 * H * W * (world - 1) / max(world, 1))}
             del band
