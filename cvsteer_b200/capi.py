@@ -92,6 +92,10 @@ _SIGS = {
     "cvs_g2_run_batch_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t,
                                         C.c_uint, C.POINTER(C.c_void_p), C.c_size_t, C.c_size_t]),
     "cvs_enable_peer_access": (C.c_int, [C.c_int, C.c_int]),
+    "cvs_shared_alloc": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]),
+    "cvs_shared_open": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "cvs_shared_close": (C.c_int, [C.c_int, C.c_void_p]),
+    "cvs_shared_free": (C.c_int, [C.c_int, C.c_void_p]),
     "cvs_g4_run_batch_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t,
                                         C.c_uint, C.c_int, C.c_float, C.POINTER(C.c_void_p), C.c_size_t, C.c_size_t]),
     "cvs_to_u8_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_float, C.c_void_p,

@@ -68,6 +68,47 @@ extern "C" int cvs_enable_peer_access(int device, int peer_device)
     return CVS_OK;
 }
 
+static_assert(sizeof(cudaIpcMemHandle_t) == CVS_IPC_HANDLE_BYTES, "IPC handle size");
+extern "C" int cvs_shared_alloc(int device, size_t bytes, void** ptr, unsigned char handle[CVS_IPC_HANDLE_BYTES])
+{
+    if (!ptr || !handle || !bytes) return fail(CVS_ERR_INVALID_ARG, "null argument");
+    CU_TRY(cudaSetDevice(device));
+    void* p = nullptr;
+    CU_TRY(cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        CU_TRY(e);
+    }
+    memcpy(handle, &h, sizeof(h));
+    *ptr = p;
+    return CVS_OK;
+}
+extern "C" int cvs_shared_open(int device, const unsigned char handle[CVS_IPC_HANDLE_BYTES], void** ptr)
+{
+    if (!ptr || !handle) return fail(CVS_ERR_INVALID_ARG, "null argument");
+    CU_TRY(cudaSetDevice(device));  // the IMPORTER's GPU: the mapping (and the peer path to the owner) is made for it
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    CU_TRY(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return CVS_OK;
+}
+extern "C" int cvs_shared_close(int device, void* ptr)
+{
+    if (!ptr) return CVS_OK;
+    CU_TRY(cudaSetDevice(device));
+    CU_TRY(cudaIpcCloseMemHandle(ptr));
+    return CVS_OK;
+}
+extern "C" int cvs_shared_free(int device, void* ptr)
+{
+    if (!ptr) return CVS_OK;
+    CU_TRY(cudaSetDevice(device));
+    CU_TRY(cudaFree(ptr));
+    return CVS_OK;
+}
+
 extern "C" int cvs_g2_make_taps(int which, int width, float spacing, float* dst)
 {
     if (which < 0 || which >= G2_NUM_TAPSETS || width < 1 || width > MAX_WIDTH || !dst)

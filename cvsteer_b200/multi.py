@@ -112,39 +112,46 @@ def plane_layout(names: Sequence[str], rows_per_level: Sequence[int], cols: int)
     return out, off
 
 
+class _RawCuda:
+    """A device pointer dressed as a __cuda_array_interface__ exporter so that torch can alias it without copying."""
+
+    def __init__(self, ptr: int, nelem: int):
+        self.__cuda_array_interface__ = {"shape": (nelem,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
 class PeerPlanes:
     """Root-owned full-size output planes of a band run, mapped into every rank over CUDA IPC (NVLink peer memory).
 
     full[level][name] is a [rows_l, cols_l] fp32 tensor on every rank: real memory on `root`, a peer mapping of the
-    same memory elsewhere.  Create once per (image size, plane set) and reuse across steps -- opening IPC handles
-    costs milliseconds.  Ranks must call `fence()` after their kernels before the root reads the planes."""
+    same memory elsewhere.  The block is allocated and exported by the C library (cvs_shared_alloc) and opened by
+    every other rank with ITS OWN GPU current (cvs_shared_open) -- that is what makes the mapping usable by that
+    GPU's kernels.  Create once per (image size, plane set) and reuse across steps; call close() (collective) when
+    done.  Ranks call `fence()` after their kernels before the root reads the planes."""
 
     def __init__(self, names: Sequence[str], rows: int, cols: int, levels: int, root: int = 0, group=None):
-        from torch.multiprocessing.reductions import reduce_tensor
+        import ctypes as C
+
+        from . import capi
         self.root, self.group = root, group
-        rank = dist.get_rank(group)
+        self.rank = dist.get_rank(group)
+        self.device = torch.cuda.current_device()
         self.names = list(names)
         self.layout, total = plane_layout(self.names, level_rows(rows, levels), cols)
-        self._flat = None
+        lib, ptr = capi.lib(), C.c_void_p()
         obj = [None]
-        if rank == root:
-            self._flat = torch.empty(total, dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
-            obj = [reduce_tensor(self._flat)]
+        if self.rank == root:
+            handle = C.create_string_buffer(64)
+            capi.check(lib.cvs_shared_alloc(self.device, total * 4, C.byref(ptr), handle))
+            obj = [handle.raw]
         dist.broadcast_object_list(obj, src=root, group=group)
-        if rank != root:
-            rebuild, args = obj[0]
-            here = torch.cuda.current_device()
-            self._flat = rebuild(*args)   # cudaIpcOpenMemHandle inside torch (opened on the OWNER's device index)
-            torch.cuda.set_device(here)
-            # torch maps the block in the owner's context, which does not give THIS rank's GPU access to it: enable the
-            # NVLink peer path explicitly, or the first remote store faults with an illegal address.
-            if self._flat.device.index != here:
-                from . import capi
-                capi.check(capi.lib().cvs_enable_peer_access(here, self._flat.device.index))
+        if self.rank != root:
+            capi.check(lib.cvs_shared_open(self.device, obj[0], C.byref(ptr)))
+        self._ptr = ptr.value
+        self._flat = torch.as_tensor(_RawCuda(self._ptr, total), device=torch.device("cuda", self.device))
         self.full: List[Dict[str, torch.Tensor]] = [dict() for _ in range(levels)]
         for (l, n), (off, r, c) in self.layout.items():
             self.full[l][n] = self._flat[off:off + r * c].view(r, c)
-        dist.barrier(group)               # nobody proceeds (or frees) before every rank holds its mapping
+        dist.barrier(group)               # nobody proceeds before every rank holds its mapping
 
     def rows_of(self, level: int, lo: int, hi: int) -> Dict[str, torch.Tensor]:
         """Views of rows [lo, hi) of every plane of `level` (contiguous row blocks)."""
@@ -154,6 +161,20 @@ class PeerPlanes:
         """All ranks' stores have landed in the root's memory when this returns on the root."""
         torch.cuda.current_stream().synchronize()   # kernel completion flushes its peer stores (system-scope release)
         dist.barrier(self.group)
+
+    def close(self):
+        """Collective: importers unmap, then the owner frees.  Tensors handed out by `full` are invalid afterwards."""
+        from . import capi
+        if self._ptr is None:
+            return
+        torch.cuda.synchronize()
+        self.full, self._flat = [], None
+        if self.rank != self.root:
+            capi.check(capi.lib().cvs_shared_close(self.device, self._ptr))
+        dist.barrier(self.group)
+        if self.rank == self.root:
+            capi.check(capi.lib().cvs_shared_free(self.device, self._ptr))
+        self._ptr = None
 
 
 def run_bands(load_rows: Callable[[int, int], torch.Tensor], rows: int, cols: int, levels: int, process: ProcessBand,

@@ -106,6 +106,15 @@ CVS_API int cvs_device_count(int* count);
  * output planes of another GPU mapped through CUDA IPC: the row-band mode then stores each band straight into the root
  * GPU's planes from inside the fused kernel.  Idempotent; CVS_ERR_CUDA when the two GPUs have no peer path. */
 CVS_API int cvs_enable_peer_access(int device, int peer_device);
+/* Device memory that other PROCESSES on this node can map (one process per GPU): the owner allocates and exports a
+ * 64-byte CUDA IPC handle; every other rank opens it WITH ITS OWN GPU CURRENT, which also sets up the NVLink peer
+ * mapping, and gets a pointer its kernels can store through.  cvs_shared_close unmaps (importers), cvs_shared_free
+ * releases (owner, after every importer has closed). */
+#define CVS_IPC_HANDLE_BYTES 64
+CVS_API int cvs_shared_alloc(int device, size_t bytes, void** ptr, unsigned char handle[CVS_IPC_HANDLE_BYTES]);
+CVS_API int cvs_shared_open(int device, const unsigned char handle[CVS_IPC_HANDLE_BYTES], void** ptr);
+CVS_API int cvs_shared_close(int device, void* ptr);
+CVS_API int cvs_shared_free(int device, void* ptr);
 
 /* ---- taps: SteerableFilters::create (cvsteer/SteerableFilters.cpp:33-42) with the reference's tap
  *      functions G21..G23,H21..H24 (G2.cpp:35-42) / G41..G45,H41..H46 (G4.cpp:34-45).  Host-only.

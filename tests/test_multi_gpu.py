@@ -51,7 +51,8 @@ def _worker_body(rank, world, port, q, backend):
         ok = ok and all(torch.equal(full2[l][k], whole[l][k][0]) for l in range(L) for k in full2[l])
         q.put(ok)
     dist.barrier()
-    del peer, full2
+    del full2
+    peer.close()
     dist.destroy_process_group()
 
 

@@ -102,7 +102,7 @@ def main():
             if world > 1:   # compute and gather fused: each rank's kernels store into the root's planes over NVLink peer memory
                 peer = multi.PeerPlanes(["theta", "strength", "e"], H, W, L)
                 t_d = timed(lambda: multi.run_bands(lambda lo_, hi_: band, H, W, L, process, down, gather="direct", peer=peer), 1, a.steps, world, dev)
-                del peer
+                peer.close()
             line = {"config": "cfg5", "what": "%dx%d image, G2/H2 M1 + 5-level pyramid, %d row bands + halo" % (H, W, world), "n_gpus": world,
                     "compute_only_ms": round(t_c, 3), "compute_plus_gather_ms": round(t_g, 3),
                     "fused_peer_store_ms": None if t_d is None else round(t_d, 3),

@@ -44,7 +44,8 @@ try:
         ok = all(torch.equal(full[l][k], whole[l][k][0]) for l in range(L) for k in full[l])
         say("bitwise equal to the whole-image run:", ok)
     dist.barrier()
-    del peer, full
+    del full
+    peer.close()
     say("teardown")
     dist.destroy_process_group()
     say("exit")
