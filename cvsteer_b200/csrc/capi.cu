@@ -281,13 +281,20 @@ int geom_from_batch(const cvs_batch* b, BatchGeom* g)
     return CVS_OK;
 }
 
-// The band contract for a filter of radius R: the buffer must hold image rows [out_row_begin-R, out_row_end+R) clipped to
-// the image.
-int check_band(const BatchGeom& g, int radius, int full_rows_out_level)
+// The band contract: the buffer must hold every image row the requested output rows read, i.e. rows
+// [need_lo, need_hi) = the filter footprint of [out_row_begin, out_row_end) clipped to the image (reflect-101 only ever
+// folds back INTO that clipped interval).  stride = 1: a (2*radius+1)-tap filter at the same level; stride = 2: pyr_down,
+// whose output row y reads input rows 2y-2 .. 2y+2.  A violation would not fault (the loaders clamp) but silently
+// filter zeros, so it is an argument error.
+int check_band(const BatchGeom& g, int radius, int full_rows_out_level, int stride = 1)
 {
     if (g.out_row_begin < 0 || g.out_row_end > full_rows_out_level || g.out_row_begin >= g.out_row_end)
         return fail(CVS_ERR_INVALID_ARG, "output rows [%d,%d) invalid", g.out_row_begin, g.out_row_end);
-    (void)radius;
+    const long long lo = (long long)stride * g.out_row_begin - radius, hi = (long long)stride * (g.out_row_end - 1) + radius + 1;
+    const long long need_lo = lo < 0 ? 0 : lo, need_hi = hi > g.full_rows ? g.full_rows : hi;
+    if (g.y_origin > need_lo || (long long)g.y_origin + g.buf_rows < need_hi)
+        return fail(CVS_ERR_INVALID_ARG, "band buffer holds image rows [%d,%d) but output rows [%d,%d) need [%lld,%lld)", g.y_origin,
+                    g.y_origin + g.buf_rows, g.out_row_begin, g.out_row_end, need_lo, need_hi);
     return CVS_OK;
 }
 
@@ -655,7 +662,7 @@ extern "C" int cvs_pyr_down_dev(int device, const cvs_batch* b, float* out, void
         g.out_row_end = (g.full_rows + 1) / 2;
         g.out_row_origin = 0;
     }
-    rc = check_band(g, 2, (g.full_rows + 1) / 2);
+    rc = check_band(g, 2, (g.full_rows + 1) / 2, 2);
     if (rc) return rc;
     CU_TRY(cudaSetDevice(device));
     CU_TRY(launch_pyr_down(g, out, static_cast<cudaStream_t>(stream)));
