@@ -99,6 +99,14 @@ enum { MARCH_TW = 128, MARCH_MAX_OUT = 20 };
 // halo is the radius rounded up to 4 floats, and the row pitch follows.
 __host__ __device__ constexpr int march_halo_left(int R) { return (R + 3) & ~3; }
 __host__ __device__ constexpr int march_tile_width(int R) { return MARCH_TW + 2 * march_halo_left(R); }
+// 8-bit input staged by TMA: the box starts 16 BYTES left of the strip (start coordinates must be multiples of 16 bytes),
+// so a raw tile row is 128 + 2 * 16 bytes; it is expanded to the fp32 tile in shared memory before the march.
+enum { MARCH_U8_HALO = 16, MARCH_U8_TW = MARCH_TW + 2 * MARCH_U8_HALO };
+__host__ __device__ constexpr int march_smem_bytes(int R, int BH, bool tma_u8)
+{
+    const int f32 = (BH + 2 * R) * march_tile_width(R) * 4 + 16;  // fp32 tile + mbarrier
+    return tma_u8 ? ((f32 + 127) & ~127) + (BH + 2 * R) * MARCH_U8_TW : f32;
+}
 
 struct MarchArgs {
     // input: n frames, rows are buffer rows; element (f, r, c) at in + f*in_frame_stride + r*in_pitch + c (bytes for
@@ -377,6 +385,8 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
     const int ytop = yb - R;                           // image row of tile row 0
 
     if (USE_TMA) {
+        constexpr bool U8 = sizeof(TIn) == 1;
+        unsigned char* raw = smem_raw + ((sizeof(float) * TROWS * TWH + 16 + 127) & ~size_t(127));  // 8-bit staging area (U8 only)
         if (threadIdx.x == 0) {
             ptx::prefetch_tmap(&tmap);
             ptx::mbar_init(bar, 1);
@@ -384,10 +394,28 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            ptx::mbar_arrive_expect_tx(bar, TROWS * TWH * sizeof(float));
-            ptx::tma_load_3d(tile, &tmap, x0 - march_halo_left(R), ytop - a.y_origin, frame, bar);
+            if constexpr (U8) {
+                ptx::mbar_arrive_expect_tx(bar, TROWS * MARCH_U8_TW);
+                ptx::tma_load_3d(raw, &tmap, x0 - MARCH_U8_HALO, ytop - a.y_origin, frame, bar);
+            } else {
+                ptx::mbar_arrive_expect_tx(bar, TROWS * TWH * sizeof(float));
+                ptx::tma_load_3d(tile, &tmap, x0 - march_halo_left(R), ytop - a.y_origin, frame, bar);
+            }
         }
         ptx::mbar_wait(bar, 0);
+        if constexpr (U8) {
+            // expand bytes -> fp32 tile: a thread owns tile columns t and t + NT for every row (TMA zero-filled the
+            // out-of-image part, which patch_reflect overwrites below exactly as for fp32 input)
+            static_assert(TWH <= 2 * NT, "two tile columns per thread");
+            const int c0 = threadIdx.x, c1 = threadIdx.x + NT;
+            const unsigned char* rp = raw + (MARCH_U8_HALO - march_halo_left(R));
+#pragma unroll 8
+            for (int rt = 0; rt < TROWS; ++rt, rp += MARCH_U8_TW) {
+                tile[rt * TWH + c0] = (float)rp[c0];
+                if (c1 < TWH) tile[rt * TWH + c1] = (float)rp[c1];
+            }
+            __syncthreads();
+        }
         patch_reflect<R, TWH, TROWS>(tile, x0, ytop, a.cols, a.full_rows, NT);
     } else {
         load_tile_manual<R, TWH, TROWS, TIn>(tile, a, frame, x0, ytop, NT);

@@ -38,7 +38,7 @@ static inline PFN_encodeTiled get_encode_fn()
     return fn;
 }
 
-// 3-D fp32 tensor (x = cols, y = buffer rows, z = frames); box = (box_w, box_h, 1); OOB -> zeros.
+// 3-D fp32 (or 8-bit) tensor (x = cols, y = buffer rows, z = frames); box = (box_w, box_h, 1) elements; OOB -> zeros.
 static inline bool make_tmap(CUtensorMap* m, const BatchGeom& g, int box_w, int box_h)
 {
     PFN_encodeTiled enc = get_encode_fn();
@@ -47,7 +47,7 @@ static inline bool make_tmap(CUtensorMap* m, const BatchGeom& g, int box_w, int 
     cuuint64_t strides[2] = {(cuuint64_t)g.in_pitch, (cuuint64_t)(g.n > 1 ? g.in_frame_stride : g.in_pitch * (size_t)g.buf_rows)};
     cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(g.in), dims, strides, box, estr,
+    CUresult r = enc(m, g.in_u8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(g.in), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
@@ -57,7 +57,6 @@ static inline bool tma_eligible(const BatchGeom& g, int R)
 {
     static const bool force_ldg = getenv("CVS_FORCE_LDG") != nullptr;  // A/B switch for profiling the two loaders
     if (force_ldg) return false;
-    if (g.in_u8) return false;
     if (((uintptr_t)g.in & 15) || (g.in_pitch & 15) || (g.in_frame_stride & 15)) return false;
     if (g.cols < R + 1 || g.full_rows < R + 1) return false;  // one reflect fold must land inside the tile
     if (g.n > 1 && g.in_frame_stride < g.in_pitch * (size_t)g.buf_rows) return false;
@@ -83,8 +82,7 @@ template <class Fam, unsigned MASK, bool TMA, typename TIn, bool BAKED, int PX =
 static cudaError_t launch_march_one(const CUtensorMap& tm, const MarchArgs& a, const TapTable<Fam::NSETS, Fam::R>& tt, dim3 grid,
                                     cudaStream_t stream, LaunchInfo* info, const char* name)
 {
-    constexpr int TROWS = Fam::BH + 2 * Fam::R, TWH = march_tile_width(Fam::R);
-    constexpr int smem = TROWS * TWH * (int)sizeof(float) + 16;
+    constexpr int smem = march_smem_bytes(Fam::R, Fam::BH, TMA && sizeof(TIn) == 1);
     auto kfn = k_march<Fam, MASK, TMA, TIn, BAKED, PX>;
     static std::once_flag once;  // one per instantiation
     static cudaError_t attr_err = cudaSuccess;
@@ -141,7 +139,11 @@ static cudaError_t launch_march_mask(const BatchGeom& g, const MarchArgs& a, con
     memset(&tm, 0, sizeof(tm));
     constexpr int TROWS = Fam::BH + 2 * Fam::R, TWH = march_tile_width(Fam::R);
     char nm[96];
-    if (tma_eligible(g, Fam::R) && make_tmap(&tm, g, TWH, TROWS)) {
+    if (g.in_u8 && tma_eligible(g, Fam::R) && make_tmap(&tm, g, MARCH_U8_TW, TROWS)) {
+        snprintf(nm, sizeof(nm), "%s/tma-u8", name);
+        return launch_march_one<Fam, MASK, true, unsigned char, false>(tm, a, tt, grid, stream, info, nm);
+    }
+    if (!g.in_u8 && tma_eligible(g, Fam::R) && make_tmap(&tm, g, TWH, TROWS)) {
         if constexpr (BAKED_OK) {
             if (taps_are_baked<Fam>(tt)) {
                 if constexpr (PX2_OK) {

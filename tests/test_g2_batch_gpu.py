@@ -492,3 +492,23 @@ def test_random_sweep_vs_oracle(seed):
                 assert_close_range(res[k][i].cpu().numpy(), w[j], s, f"{k} seed{seed}")
         if "phase" in res:
             assert_angle_close(res["phase"][i].cpu().numpy(), w[4], w[3], 2 * np.pi, f"phase seed{seed}")
+
+
+def test_u8_tma_loader_matches_float_and_ldg_bitwise():
+    """8-bit frames TMA can describe (16-byte aligned base and pitch) are staged as bytes and expanded in shared memory:
+    same results, bit for bit, as the fp32 input and as the cooperative 8-bit loader; G4 too."""
+    from cvsteer_b200.batch import G4Batch
+    img8 = np.random.default_rng(41).integers(0, 256, (3, 150, 256), dtype=np.uint8)
+    x8 = torch.from_numpy(img8).cuda()
+    xf = x8.float()
+    pad = torch.zeros((3, 150, 259), dtype=torch.uint8, device="cuda")
+    pad[:, :, 1:257] = x8
+    for g, mask in ((G2Batch(), capi.G2_MASK_FULL), (G2Batch(), capi.G2_MASK_LINES), (G2Batch(), (1 << capi.G2_NPLANES) - 1),
+                    (G4Batch(), capi.G4_MASK_BASIS)):
+        a = g.run(x8, mask)
+        assert g.last_launch()["kernel"].endswith("/tma-u8"), g.last_launch()["kernel"]
+        b = g.run(xf, mask)
+        c = g.run(pad[:, :, 1:257], mask)
+        assert g.last_launch()["kernel"].endswith("/ldg-u8")
+        for k in a:
+            assert torch.equal(a[k], b[k]) and torch.equal(a[k], c[k]), (k, hex(mask))
