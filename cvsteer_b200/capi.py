@@ -91,6 +91,7 @@ _SIGS = {
     "cvs_pyr_down_dev": (C.c_int, [C.c_int, C.POINTER(Batch), C.c_void_p, C.c_void_p]),
     "cvs_g2_run_batch_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t,
                                         C.c_uint, C.POINTER(C.c_void_p), C.c_size_t, C.c_size_t]),
+    "cvs_plan_bands": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "cvs_enable_peer_access": (C.c_int, [C.c_int, C.c_int]),
     "cvs_shared_alloc": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]),
     "cvs_shared_open": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]),

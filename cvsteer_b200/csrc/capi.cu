@@ -1011,6 +1011,21 @@ int run_band_on_device(int device, int width, float spacing, const BandPlanC& pl
 }
 }  // namespace
 
+extern "C" int cvs_plan_bands(int rows, int world, int levels, int radius, int* plan, int* rows_per_level)
+{
+    if (rows <= 0 || world <= 0 || levels <= 0 || levels > 30 || radius < 0 || !plan) return fail(CVS_ERR_INVALID_ARG, "cvs_plan_bands: bad argument");
+    const std::vector<BandPlanC> plans = plan_bands_c(rows, world, levels, radius);
+    for (int r = 0; r < world; ++r)
+        for (int l = 0; l < levels; ++l) {
+            int* q = plan + ((size_t)r * levels + l) * 4;
+            q[0] = plans[r].out[l].first, q[1] = plans[r].out[l].second;
+            q[2] = plans[r].have[l].first, q[3] = plans[r].have[l].second;
+        }
+    if (rows_per_level)
+        for (int l = 0; l < levels; ++l) rows_per_level[l] = plans[0].rows[l];
+    return CVS_OK;
+}
+
 extern "C" int cvs_g2_run_bands_host_multi(int n_devices, const int* devices, int width, float spacing, const float* image, int rows, int cols,
                                            size_t step, int levels, unsigned mask, float* const* const* outs, const size_t* out_steps)
 {

@@ -246,6 +246,13 @@ CVS_API int cvs_g2_run_batch_host_multi(int n_devices, const int* devices, int w
                                         int rows, int cols, size_t in_step, size_t in_frame_stride, unsigned mask,
                                         float* const* outs, size_t out_step, size_t out_frame_stride);
 
+/* The row-band plan both band paths use (this library's multi-GPU entry point below and cvsteer_b200/multi.py), for
+ * callers that shard one huge image over one process per GPU themselves.  Band edges sit on multiples of 2^(levels-1)
+ * rows; per rank r and pyramid level l, plan[(r*levels + l)*4 + {0,1,2,3}] = out_lo, out_hi (rows of level l the rank
+ * PRODUCES) and have_lo, have_hi (rows of level l it must hold: outputs + filter halo `radius` + what pyr_down of the
+ * next level reads).  rows_per_level[l] = image height at level l.  Ranks past the end of the image get empty ranges. */
+CVS_API int cvs_plan_bands(int rows, int world, int levels, int radius, int* plan, int* rows_per_level);
+
 /* One very large image split into ROW BANDS over `n_devices` GPUs of this process.  Band
  * edges sit on multiples of 2^(levels-1) rows; every GPU uploads its band plus the halo its coarsest level needs straight
  * from the host image (no halo exchange), builds its slice of the `levels`-level pyramid in band mode, runs the fused

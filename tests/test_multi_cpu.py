@@ -144,3 +144,31 @@ def test_plane_layout_for_peer_planes():
     assert all(off % 32 == 0 for off, _ in spans)
     assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:])) and spans[-1][1] <= total
     assert lay[(0, "theta")][1:] == (1001, 701) and lay[(1, "e")][1:] == (501, 351) and lay[(4, "e")][1:] == (63, 44)
+
+
+def test_c_band_plan_equals_python_plan():
+    """cvs_plan_bands (what cvs_g2_run_bands_host_multi shards by, exported for C/C++ callers) == multi.plan_bands."""
+    import ctypes as C
+
+    from cvsteer_b200 import capi
+    lib = capi.lib()
+    n = 0
+    for rows in (5, 17, 64, 100, 777, 1000, 4097, 32768):
+        for world in (1, 2, 3, 8):
+            for levels in (1, 2, 4, 5):
+                for radius in (4, 6):
+                    plan = (C.c_int * (world * levels * 4))()
+                    hl = (C.c_int * levels)()
+                    capi.check(lib.cvs_plan_bands(rows, world, levels, radius, plan, hl))
+                    assert list(hl) == multi.level_rows(rows, levels)
+                    for p in multi.plan_bands(rows, world, levels, radius):
+                        for l in range(levels):
+                            q = plan[(p.rank * levels + l) * 4:(p.rank * levels + l) * 4 + 4]
+                            for got, want in ((tuple(q[:2]), p.out[l]), (tuple(q[2:]), p.have[l])):
+                                if want[0] >= want[1]:
+                                    assert got[0] >= got[1], (rows, world, levels, radius, p.rank, l, got, want)
+                                else:
+                                    assert got == tuple(want), (rows, world, levels, radius, p.rank, l, got, want)
+                            n += 1
+    assert n > 1000
+    assert lib.cvs_plan_bands(0, 1, 1, 4, plan, None) == capi.ERR_INVALID_ARG
