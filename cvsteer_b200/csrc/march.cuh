@@ -33,12 +33,19 @@
 // 1: the slot dispatch of the rolled loop is a balanced compare tree instead of a switch (which nvcc lowers to a
 // constant-memory jump table: LDC + BRX on the critical path of every row).
 // masks with at most this many planes keep a 64-bit base per plane in registers (2 registers each)
-// Two pixels per thread for the issue-bound static masks (see k_march's PX).  Off by default: 198 instead of 217
-// instructions per pixel-row, but the K-fold unrolled body grows to 57 KB and falls out of the instruction cache
-// (M2 138.9 -> 118.6, M1 194 -> 138 Gpix/s); with the rolled loop it does win (M2 130.9 -> 135.6, M1 172 -> 178) but stays
-// below the unrolled one-pixel kernel.  Kept for builds that trade the unrolled body away (build_variant.sh).
+// Two pixels per thread (see k_march's PX): 0 = nowhere, 1 = the M2 kernel (default), 2 = M1 as well.
+// 198 instead of 217 instructions per pixel-row, but with the K-fold unrolled body the loop grows to 57 KB and falls out of
+// the instruction cache (M2 138.9 -> 118.6 Gpix/s); it pays together with the shift loop below (27 KB body, 209
+// instructions per pixel-row): M2 138.9 -> 143.2 Gpix/s at 1080p, 134.7 -> 139.7 at 4K.  M1 (short epilogue) loses 1-2 %
+// that way, so it keeps the unrolled one-pixel kernel.
 #ifndef CVS_MARCH_PX2
-#define CVS_MARCH_PX2 0
+#define CVS_MARCH_PX2 1
+#endif
+// With two-pixel threads: replace the K-fold unrolled body by a "shift" loop -- U row bodies on a LINEAR register window
+// (2R old rows + U new ones), then 2R x NROW x PX register moves shift the window down by U.  Body = U x 2 x ~200
+// instructions (U = 4: 27 KB, inside the instruction cache) at the price of 2R*NROW/U moves per pixel-row.  0 = off.
+#ifndef CVS_MARCH_SHIFT_U
+#define CVS_MARCH_SHIFT_U 4
 #endif
 #ifndef CVS_CURSOR_MAX_PLANES
 #define CVS_CURSOR_MAX_PLANES 8
@@ -535,7 +542,71 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
         cur.next_row();
     };
     int rt_done = 0;  // tile rows already consumed by the unrolled path below (always a multiple of K)
-    if constexpr (CVS_MARCH_UNROLL_EPILOGUE && MASK != 0 && !Fam::SHARED_ROW_PASS) {
+    constexpr bool SHIFT = CVS_MARCH_SHIFT_U > 0 && PX == 2 && MASK != 0 && !Fam::SHARED_ROW_PASS;
+    if constexpr (SHIFT) {
+        constexpr int U = CVS_MARCH_SHIFT_U > 0 ? CVS_MARCH_SHIFT_U : 1, W2 = 2 * R;
+        float lw[NROW][W2 + U][PX];  // linear window: [0, 2R) = the 2R rows above the newest ones, oldest first; [2R, 2R+U) = new rows
+        const int total = nrows + W2;
+        auto push = [&](auto pos_c) {
+            constexpr int pos = decltype(pos_c)::value;
+#pragma unroll
+            for (int p = 0; p < NROW; ++p)
+#pragma unroll
+                for (int px = 0; px < PX; ++px) lw[p][pos][px] = r[p][px];
+        };
+        auto col_lin = [&](auto u_c) {  // the output row whose newest window row sits at position 2R + u
+            constexpr int u = decltype(u_c)::value;
+#pragma unroll
+            for (int px = 0; px < PX; ++px) {
+#pragma unroll
+                for (int q = 0; q < NB; ++q) {
+                    const int rp = Fam::basis_row(q), set = Fam::basis_set(q);
+                    auto w = [&](int k) -> float { return lw[rp][u + R + k][px]; };
+                    float acc;
+                    if (Fam::basis_odd(q)) {
+                        acc = tap(set, 1) * (w(1) - w(-1));
+#pragma unroll
+                        for (int i = 2; i <= R; ++i) acc = fmaf(tap(set, i), w(i) - w(-i), acc);
+                    } else {
+                        acc = tap(set, 0) * w(0);
+#pragma unroll
+                        for (int i = 1; i <= R; ++i) acc = fmaf(tap(set, i), w(i) + w(-i), acc);
+                    }
+                    b[px][q] = acc;
+                }
+            }
+        };
+        auto shift = [&](auto by_c) {
+            constexpr int by = decltype(by_c)::value;
+#pragma unroll
+            for (int p = 0; p < NROW; ++p)
+#pragma unroll
+                for (int i = 0; i < W2; ++i)
+#pragma unroll
+                    for (int px = 0; px < PX; ++px) lw[p][i][px] = lw[p][i + by][px];
+        };
+        [&]<int... I>(std::integer_sequence<int, I...>) {
+            ((row_pass(I), push(std::integral_constant<int, I>{})), ...);
+        }(std::make_integer_sequence<int, W2>{});
+        int rt = W2;
+#pragma unroll 1
+        for (; rt + U <= total; rt += U) {  // unchecked groups of U output rows: one basic block
+            [&]<int... I>(std::integer_sequence<int, I...>) {
+                ((row_pass(rt + I), push(std::integral_constant<int, W2 + I>{}), col_lin(std::integral_constant<int, I>{}), emit_row(0.f)), ...);
+            }(std::make_integer_sequence<int, U>{});
+            shift(std::integral_constant<int, U>{});
+        }
+#pragma unroll 1
+        for (; rt < total; ++rt) {  // fewer than U rows left (last band of an image): one row per iteration
+            row_pass(rt);
+            push(std::integral_constant<int, W2>{});
+            col_lin(std::integral_constant<int, 0>{});
+            emit_row(0.f);
+            shift(std::integral_constant<int, 1>{});
+        }
+        rt_done = total;
+    }
+    if constexpr (CVS_MARCH_UNROLL_EPILOGUE && MASK != 0 && !Fam::SHARED_ROW_PASS && !SHIFT) {
         // Variant for short epilogues: the whole row body (row pass, column pass, epilogue) is replicated per slot, so the
         // loop needs no slot dispatch at all.  Only worth it while K x (body) still fits the instruction cache.
         // Groups of K rows run WITHOUT per-row bounds checks, i.e. as one basic block that the scheduler can overlap
@@ -564,6 +635,7 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
             }
         }
     }
+    if constexpr (!SHIFT) {
     int slot = 0;  // rt_done is a multiple of K, so the window slot of tile row rt_done is 0 again
     float theta_next = 0.f;
     if (Fam::template reads_theta_map<MASK>(a) && rt_done >= 2 * R && rt_done < nrows + 2 * R) theta_next = cur.theta(a);
@@ -598,6 +670,7 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
         slot = (slot + 1 == K) ? 0 : slot + 1;
         if (rt >= 2 * R) emit_row(theta_px);
     }
+    }  // !SHIFT
     if (a.pyr_out) emit_next_level<R, BH, NT>(tile, a, frame, x0, yb);  // CTA-uniform; the tile is read-only after staging
 }
 

@@ -14,8 +14,8 @@ cudaError_t launch_march_g2(const FamilyTaps& taps, const BatchGeom& g, const Ma
     const int out_rows = g.out_row_end - g.out_row_begin;
     const dim3 grid((g.cols + MARCH_TW - 1) / MARCH_TW, (out_rows + G2Fam::BH - 1) / G2Fam::BH, g.n);
     const unsigned mask = a.mask;
-    if (dom && mask == CVS_G2_MASK_ORIENT) return launch_march_mask<G2Fam, CVS_G2_MASK_ORIENT, true, CVS_MARCH_PX2 != 0>(g, a, tt, grid, stream, info, "g2_march<M1>");
-    if (dom && mask == CVS_G2_MASK_FULL) return launch_march_mask<G2Fam, CVS_G2_MASK_FULL, true, CVS_MARCH_PX2 != 0>(g, a, tt, grid, stream, info, "g2_march<M2>");
+    if (dom && mask == CVS_G2_MASK_ORIENT) return launch_march_mask<G2Fam, CVS_G2_MASK_ORIENT, true, (CVS_MARCH_PX2 > 1)>(g, a, tt, grid, stream, info, "g2_march<M1>");
+    if (dom && mask == CVS_G2_MASK_FULL) return launch_march_mask<G2Fam, CVS_G2_MASK_FULL, true, (CVS_MARCH_PX2 > 0)>(g, a, tt, grid, stream, info, "g2_march<M2>");
     if (dom && mask == CVS_G2_MASK_STATE) return launch_march_mask<G2Fam, CVS_G2_MASK_STATE, true>(g, a, tt, grid, stream, info, "g2_march<M0>");
     static const bool no_lines = getenv("CVS_NO_STATIC_LINES") != nullptr;  // A/B switch
     if (dom && mask == CVS_G2_MASK_LINES && !no_lines) return launch_march_g2_lines(g, a, tt, grid, stream, info);
