@@ -84,6 +84,8 @@ class _FusedBatch:
         next_level: optional contiguous float32 [n, (rows+1)//2, (cols+1)//2]; the same launch fills it with
         cv::pyrDown(frames) from the tile it stages anyway (whole frames only)."""
         x = _as_batch(frames)
+        if x.device.index != self.device:
+            raise capi.CvsError(capi.ERR_INVALID_ARG, f"frames live on cuda:{x.device.index}, this handle on cuda:{self.device}")
         n, rows, cols = x.shape
         out_rows = rows if band is None else band.row_end - band.row_begin
         nplanes = len(self._names)
@@ -93,13 +95,18 @@ class _FusedBatch:
         arr = (C.c_void_p * nplanes)()
         for p in planes:
             t = outs[p]
-            if t.shape != (n, out_rows, cols) or t.dtype != torch.float32 or not t.is_contiguous():
-                raise capi.CvsError(capi.ERR_SIZE_MISMATCH, f"output plane {p}: need contiguous float32 {(n, out_rows, cols)}")
+            if t.shape != (n, out_rows, cols) or t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda:
+                raise capi.CvsError(capi.ERR_SIZE_MISMATCH, f"output plane {p}: need contiguous CUDA float32 {(n, out_rows, cols)}")
             arr[p] = t.data_ptr()
         tm = None
         if steer == capi.STEER_MAP:
-            if theta_map is None or tuple(theta_map.shape[-2:]) != (out_rows, cols) or not theta_map.is_contiguous():
-                raise capi.CvsError(capi.ERR_SIZE_MISMATCH, "theta_map must be contiguous float32 [n, out_rows, cols]")
+            # the kernel reads theta_map + frame * out_frame_stride: the map needs the full [n, out_rows, cols] extent
+            if theta_map is not None and theta_map.dim() == 2 and n == 1:
+                theta_map = theta_map.unsqueeze(0)
+            if (theta_map is None or tuple(theta_map.shape) != (n, out_rows, cols) or theta_map.dtype != torch.float32
+                    or not theta_map.is_contiguous() or theta_map.device != x.device):
+                raise capi.CvsError(capi.ERR_SIZE_MISMATCH,
+                                    f"theta_map must be a contiguous float32 tensor {(n, out_rows, cols)} on {x.device}")
             tm = C.c_void_p(theta_map.data_ptr())
         b = _batch_struct(x, cols * 4, out_rows * cols * 4, band)
         if next_level is not None:
@@ -109,7 +116,8 @@ class _FusedBatch:
             b.next_level = next_level.data_ptr()
             b.next_pitch, b.next_frame_stride = want[2] * 4, want[1] * want[2] * 4
         fn = getattr(self._lib, f"cvs_{self._prefix}_run_batch_dev")
-        capi.check(fn(self._h, C.byref(b), mask, steer, theta, tm, arr, _stream_ptr(stream)))
+        with torch.cuda.device(self.device):   # the C call makes the handle's GPU current; torch's current device is restored
+            capi.check(fn(self._h, C.byref(b), mask, steer, theta, tm, arr, _stream_ptr(stream)))
         return {self._names[p]: outs[p] for p in planes}
 
     def run_pyramid(self, frames: torch.Tensor, levels: int, mask: int, **kw) -> List[Dict[str, torch.Tensor]]:

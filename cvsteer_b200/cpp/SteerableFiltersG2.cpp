@@ -2,6 +2,8 @@
 // Every method names the reference lines it replaces.  No pixel arithmetic happens here.
 #include <cvsteer/SteerableFiltersG2.h>
 
+#include <cstring>
+
 #include "cvsteer_c.h"
 
 _STEER_BEGIN
@@ -90,19 +92,39 @@ void SteerableFiltersG2::steer(const cv::Point& p, float theta, float& g2, float
 
 void SteerableFiltersG2::steerImpl(const Matf* theta, float thetaScalar, Matf* g2, Matf* h2, Matf* e, Matf* magnitude, Matf* phase)
 {
-    float *pg = outp(g2, m_rows, m_cols), *ph = outp(h2, m_rows, m_cols), *pe = outp(e, m_rows, m_cols);
-    float *pm = outp(magnitude, m_rows, m_cols), *pp = outp(phase, m_rows, m_cols);
-    const size_t step = (size_t)m_cols * sizeof(float);
-    if (!theta) {
-        detail::check(cvs_g2_steer_scalar_host(m_handle, thetaScalar, pg, ph, pe, pm, pp, step), "SteerableFiltersG2::steer(float)");
-        return;
+    // The C ABI writes every requested output with ONE row step.  Mat::create() keeps an already allocated Mat of matching
+    // size -- e.g. a ROI view whose step is wider than cols*4 -- so the outputs' own steps are honoured: all equal (the
+    // normal case) -> written in place; otherwise the results land in dense temporaries and are copied row by row.
+    Matf* dst[5] = {g2, h2, e, magnitude, phase};
+    float* ptr[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t step = 0;
+    bool uniform = true;
+    for (int i = 0; i < 5; ++i) {
+        ptr[i] = outp(dst[i], m_rows, m_cols);
+        if (!dst[i]) continue;
+        if (!step) step = (size_t)dst[i]->step;
+        uniform = uniform && (size_t)dst[i]->step == step;
     }
-    if (theta->rows != m_rows || theta->cols != m_cols) detail::check(CVS_ERR_SIZE_MISMATCH, "SteerableFiltersG2::steer: theta size differs from the image");
-    // steer(getDominantOrientationAngle(), ...): the callers' idiom (example/steer.cpp:87, test/test.cpp:86).  When the
-    // argument IS our own mirror of theta_d, steer from the device-resident map instead of uploading it again.
-    const bool own = (m_mirrorValid >> 10 & 1u) && theta->ptr(0) == m_theta.ptr(0);
-    detail::check(cvs_g2_steer_map_host(m_handle, own ? nullptr : theta->ptr(0), (size_t)theta->step, pg, ph, pe, pm, pp, step),
-          "SteerableFiltersG2::steer(Mat1f)");
+    Matf tmp[5];
+    if (!uniform) {
+        step = (size_t)m_cols * sizeof(float);
+        for (int i = 0; i < 5; ++i)
+            if (dst[i]) tmp[i] = Matf(m_rows, m_cols), ptr[i] = tmp[i].ptr(0);
+    }
+    if (!theta) {
+        detail::check(cvs_g2_steer_scalar_host(m_handle, thetaScalar, ptr[0], ptr[1], ptr[2], ptr[3], ptr[4], step), "SteerableFiltersG2::steer(float)");
+    } else {
+        if (theta->rows != m_rows || theta->cols != m_cols) detail::check(CVS_ERR_SIZE_MISMATCH, "SteerableFiltersG2::steer: theta size differs from the image");
+        // steer(getDominantOrientationAngle(), ...): the callers' idiom (example/steer.cpp:87, test/test.cpp:86).  When the
+        // argument IS our own mirror of theta_d, steer from the device-resident map instead of uploading it again.
+        const bool own = (m_mirrorValid >> 10 & 1u) && theta->ptr(0) == m_theta.ptr(0);
+        detail::check(cvs_g2_steer_map_host(m_handle, own ? nullptr : theta->ptr(0), (size_t)theta->step, ptr[0], ptr[1], ptr[2], ptr[3], ptr[4], step),
+                      "SteerableFiltersG2::steer(Mat1f)");
+    }
+    if (!uniform)
+        for (int i = 0; i < 5; ++i)
+            if (dst[i])
+                for (int r = 0; r < m_rows; ++r) std::memcpy(dst[i]->ptr(r), tmp[i].ptr(r), sizeof(float) * (size_t)m_cols);
 }
 
 // G2.cpp:137-145

@@ -1,6 +1,8 @@
 // fa::SteerableFiltersG4 over the C ABI of libcvsteer_b200 (drop-in for reference cvsteer/SteerableFiltersG4.cpp).
 #include <cvsteer/SteerableFiltersG4.h>
 
+#include <cstring>
+
 #include "cvsteer_c.h"
 
 _STEER_BEGIN
@@ -12,6 +14,10 @@ cv::Mat1f taps(int which, int width, float spacing)
     cv::Mat1f k(1, 2 * width + 1);
     cvs_g4_make_taps(which, width, spacing, k.ptr(0));
     return k;
+}
+void copyRows(const cv::Mat1f& src, cv::Mat1f& dst)
+{
+    for (int r = 0; r < src.rows; ++r) std::memcpy(dst.ptr(r), src.ptr(r), sizeof(float) * (size_t)src.cols);
 }
 }  // namespace
 
@@ -57,8 +63,11 @@ void SteerableFiltersG4::steer(const cv::Mat1f& theta, cv::Mat1f& g4, cv::Mat1f&
     if (theta.rows != m_rows || theta.cols != m_cols) detail::check(CVS_ERR_SIZE_MISMATCH, "SteerableFiltersG4::steer: theta size differs from the image");
     g4.create(m_rows, m_cols);
     h4.create(m_rows, m_cols);
-    detail::check(cvs_g4_steer_map_host(m_handle, theta.ptr(0), (size_t)theta.step, g4.ptr(0), h4.ptr(0), nullptr, nullptr, (size_t)g4.step),
+    const bool same = g4.step == h4.step;  // one step for both outputs in the C ABI; differing ROI steps go through a dense copy
+    cv::Mat1f t4 = same ? h4 : cv::Mat1f(m_rows, m_cols), tg = same ? g4 : cv::Mat1f(m_rows, m_cols);
+    detail::check(cvs_g4_steer_map_host(m_handle, theta.ptr(0), (size_t)theta.step, tg.ptr(0), t4.ptr(0), nullptr, nullptr, (size_t)tg.step),
           "SteerableFiltersG4::steer(Mat1f)");
+    if (!same) copyRows(tg, g4), copyRows(t4, h4);
 }
 
 // G4.cpp:114-122
@@ -66,7 +75,10 @@ void SteerableFiltersG4::steer(float theta, cv::Mat1f& g4, cv::Mat1f& h4)
 {
     g4.create(m_rows, m_cols);
     h4.create(m_rows, m_cols);
-    detail::check(cvs_g4_steer_scalar_host(m_handle, theta, g4.ptr(0), h4.ptr(0), nullptr, nullptr, (size_t)g4.step), "SteerableFiltersG4::steer(float)");
+    const bool same = g4.step == h4.step;
+    cv::Mat1f t4 = same ? h4 : cv::Mat1f(m_rows, m_cols), tg = same ? g4 : cv::Mat1f(m_rows, m_cols);
+    detail::check(cvs_g4_steer_scalar_host(m_handle, theta, tg.ptr(0), t4.ptr(0), nullptr, nullptr, (size_t)tg.step), "SteerableFiltersG4::steer(float)");
+    if (!same) copyRows(tg, g4), copyRows(t4, h4);
 }
 
 void SteerableFiltersG4::computeDominantOrientation()

@@ -168,6 +168,9 @@ struct Filter {
     int rows = 0, cols = 0;
     size_t pitch = 0;         // bytes, multiple of 128 (TMA needs 16)
     DevBuf in, state, work, scratch;
+    cudaStream_t scratch_stream[3] = {nullptr, nullptr, nullptr};  // last stream that used each slice of `scratch` (generic widths)
+    bool scratch_used[3] = {false, false, false};
+    cudaEvent_t scratch_ev = nullptr;
     int nstate = 0;           // planes in `state`: G2 12 (7 basis, c1..c3, theta, strength); G4 11
     bool ready = false;
     bool g4_orient_ready = false;  // planes 11, 12 of a G4 handle hold theta_d / strength of the current image
@@ -221,6 +224,7 @@ int filter_destroy(Filter* f)
             cudaStreamDestroy(s);
             s = nullptr;
         }
+    if (f->scratch_ev) cudaEventDestroy(f->scratch_ev);
     f->in.release();
     f->state.release();
     f->work.release();
@@ -298,13 +302,28 @@ int check_band(const BatchGeom& g, int radius, int full_rows_out_level, int stri
     return CVS_OK;
 }
 
-int run_fused(Filter* f, const BatchGeom& g, unsigned mask, const SteerSpec& st, float* const* outs, cudaStream_t stream)
+// `slot` of `nslots`: callers that keep several launches in flight on different streams (the host-batch pipelines) give
+// each stream its own slice of the generic-width scratch; the per-frame scratch size does not depend on the chunk.
+int run_fused(Filter* f, const BatchGeom& g, unsigned mask, const SteerSpec& st, float* const* outs, cudaStream_t stream, int slot = 0,
+              int nslots = 1)
 {
     CU_TRY(cudaSetDevice(f->device));
     float* scratch = nullptr;
     if (!uses_march_path(f->family, f->taps.width)) {
-        CU_TRY(f->scratch.reserve(scratch_bytes_generic(f->family, g)));
-        scratch = static_cast<float*>(f->scratch.p);
+        const size_t per = align_up(scratch_bytes_generic(f->family, g), 256);
+        CU_TRY(f->scratch.reserve(per * (size_t)nslots));  // growing frees the old block: cudaFree waits for kernels still using it
+        scratch = reinterpret_cast<float*>(static_cast<char*>(f->scratch.p) + per * (size_t)slot);
+        // the same slice used from another stream than last time: order the two streams (device-side, no host wait)
+        if (slot < 3 && f->scratch_used[slot] && f->scratch_stream[slot] != stream) {
+            if (!f->scratch_ev) CU_TRY(cudaEventCreateWithFlags(&f->scratch_ev, cudaEventDisableTiming));
+            cudaError_t e = cudaEventRecord(f->scratch_ev, f->scratch_stream[slot]);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, f->scratch_ev, 0);
+            if (e != cudaSuccess) {  // e.g. the caller destroyed the earlier stream: fall back to a full device sync
+                cudaGetLastError();
+                CU_TRY(cudaDeviceSynchronize());
+            }
+        }
+        if (slot < 3) f->scratch_used[slot] = true, f->scratch_stream[slot] = stream;
     }
     CU_TRY(launch_basis_fused(f->family, f->taps, g, mask, st, outs, scratch, stream, &f->last));
     return CVS_OK;
@@ -495,7 +514,12 @@ extern "C" int cvs_g2_steer_point(cvs_g2* h, int x, int y, float theta, float ou
     // Fetch the 10 state values of this pixel (7 basis, c1..c3): element (y,x) of 10 consecutive planes = one strided copy.
     float v[10];
     const char* src = reinterpret_cast<const char*>(f->state.p) + (size_t)y * f->pitch + (size_t)x * 4;
-    CU_TRY(cudaMemcpy2DAsync(v, 4, src, f->pitch * f->rows, 4, 10, cudaMemcpyDeviceToHost, f->stream));
+    const size_t plane_bytes = f->pitch * f->rows;
+    if (plane_bytes < (1ull << 31)) {  // cudaMemcpy2D pitches are limited to 2 GiB (cudaDeviceProp::memPitch)
+        CU_TRY(cudaMemcpy2DAsync(v, 4, src, plane_bytes, 4, 10, cudaMemcpyDeviceToHost, f->stream));
+    } else {
+        for (int i = 0; i < 10; ++i) CU_TRY(cudaMemcpyAsync(&v[i], src + (size_t)i * plane_bytes, 4, cudaMemcpyDeviceToHost, f->stream));
+    }
     CU_TRY(cudaStreamSynchronize(f->stream));
     // The per-point overloads are host code in the reference as well (G2.cpp:115-134): a handful of scalar flops on
     // values read from the Mats.  Same expressions, same types.
@@ -731,7 +755,7 @@ int run_batch_host(Filter* f, int family, const float* in, int n, int rows, int 
         for (int p = 0; p < NPLANES; ++p)
             if (mask >> p & 1u) douts[p] = reinterpret_cast<float*>(base + (size_t)(1 + slot++) * chunk * fbytes);
         BatchGeom g = whole_frame_geom(din, false, nf, rows, cols, pitch, fbytes, pitch, fbytes);
-        int rc = run_fused(f, g, mask, st, douts, s);
+        int rc = run_fused(f, g, mask, st, douts, s, b, NBUF);
         if (rc) return rc;
         for (int p = 0; p < NPLANES; ++p)
             if (mask >> p & 1u) {
@@ -844,7 +868,7 @@ extern "C" int cvs_g2_lines_u8_host(cvs_g2* h, const uint8_t* gray, int n, int r
         BatchGeom g = whole_frame_geom(din, true, nf, rows, cols, pin, pin * rows, pf, pf * rows);
         float* outs[CVS_G2_NPLANES] = {nullptr};
         for (int i = 0; i < 3; ++i) outs[planes[i]] = reinterpret_cast<float*>(w + in_bytes + i * f_bytes);
-        int rc = run_fused(f, g, mask, st, outs, s);
+        int rc = run_fused(f, g, mask, st, outs, s, ci % nbuf, nbuf);
         if (rc) return rc;
         uint8_t* dout0 = reinterpret_cast<uint8_t*>(w + in_bytes + 3 * f_bytes);
         const bool all3 = outs8[0] && outs8[1] && outs8[2];

@@ -66,7 +66,9 @@ struct G2Fam {
     template <unsigned MASK, class Cursor>
     __device__ __forceinline__ static void epilogue(const float (&b)[NBASIS], const MarchArgs& a, const Cursor& cur, float theta_px)
     {
-        constexpr bool FAST = MASK != 0;
+        // The class state (M0: what setup() leaves behind and the getters return) takes the exact cv::cartToPolar sequence
+        // (IEEE division and sqrt, NaNs propagate): that kernel is HBM-bound, the extra ~20 instructions are free.
+        constexpr bool FAST = MASK != 0 && MASK != CVS_G2_MASK_STATE;
         const unsigned m = MASK ? MASK : a.mask;
         auto put = [&](int p, float v) { cur.put(a, p, v); };
 #pragma unroll

@@ -84,14 +84,19 @@ static cudaError_t launch_march_one(const CUtensorMap& tm, const MarchArgs& a, c
 {
     constexpr int smem = march_smem_bytes(Fam::R, Fam::BH, TMA && sizeof(TIn) == 1);
     auto kfn = k_march<Fam, MASK, TMA, TIn, BAKED, PX>;
-    static std::once_flag once;  // one per instantiation
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [&] {
-        attr_err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (attr_err == cudaSuccess)
-            attr_err = cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    });
-    if (attr_err != cudaSuccess) return attr_err;
+    // Function attributes are per DEVICE (context): one flag per (instantiation, device).  The 8-bit TMA variants ask for
+    // more than the 48 KB default, so a process that drives several GPUs must set them on each one.
+    static std::atomic<unsigned long long> done[4];  // 256 devices
+    int dev = 0;
+    if (cudaError_t e = cudaGetDevice(&dev); e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    std::atomic<unsigned long long>& word = done[(dev >> 6) & 3];
+    if (!(word.load(std::memory_order_acquire) & bit)) {
+        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        word.fetch_or(bit, std::memory_order_release);  // idempotent: a racing thread at worst sets the attributes twice
+    }
     kfn<<<grid, MARCH_TW / PX, smem, stream>>>(tm, a, tt);
     g_launches.fetch_add(1);
     if (info) {

@@ -7,6 +7,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -58,6 +59,19 @@ int main(int argc, char** argv)
         cv::Mat1f sg, sh;
         filters2.steer(0.3f, sg, sh);
         save(dir, "g2_s03", sg), save(dir, "h2_s03", sh);
+        // outputs that are views with a wider row step (a ROI of a larger Mat): create() keeps them, every row must land at
+        // the view's own step (reference: Mat expressions honour step); g2 and h2 views deliberately differ in step
+        {
+            std::vector<float> bufg((size_t)rows * (cols + 7), -1.f), bufh((size_t)rows * (cols + 3), -1.f);
+            cv::Mat1f vg(rows, cols, bufg.data(), sizeof(float) * (cols + 7)), vh(rows, cols, bufh.data(), sizeof(float) * (cols + 3));
+            filters2.steer(0.3f, vg, vh);
+            if (vg.ptr(0) != bufg.data() || vh.ptr(0) != bufh.data()) return 7;  // must not have been reallocated
+            for (int r = 0; r < rows; ++r) {
+                if (memcmp(vg.ptr(r), sg.ptr(r), sizeof(float) * cols) || memcmp(vh.ptr(r), sh.ptr(r), sizeof(float) * cols)) return 8;
+                for (int c = cols; c < cols + 3; ++c)
+                    if (bufg[(size_t)r * (cols + 7) + c] != -1.f || bufh[(size_t)r * (cols + 3) + c] != -1.f) return 9;  // padding untouched
+            }
+        }
         float pg, ph, pe, pm, pp;
         filters2.steer(cv::Point(17, 5), 0.3f, pg, ph, pe, pm, pp);
         cv::Mat1f pt(1, 5);

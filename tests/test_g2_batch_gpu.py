@@ -268,6 +268,22 @@ def test_multi_device_host_api():
             assert np.array_equal(outs[p], want[capi.G2_PLANE_NAMES[p]].cpu().numpy()), (nd, p)
 
 
+def test_generic_width_host_batch_pipeline():
+    """Non-default widths go through the two-pass generic kernels and a scratch buffer.  The host-batch pipeline keeps
+    three chunks in flight on three streams: every stream needs its own scratch slice (was one shared buffer: a race)."""
+    fr = _frames(3970, 9, 150, 230)                      # 9 frames -> 3-frame chunks round-robin on 3 streams
+    g = G2Batch(width=6, spacing=0.45)
+    dev = g.run(torch.from_numpy(fr).cuda(), capi.G2_MASK_FULL)
+    assert g.last_launch()["kernel"].startswith("generic")
+    planes = [p for p in range(capi.G2_NPLANES) if capi.G2_MASK_FULL >> p & 1]
+    xh = torch.from_numpy(fr).pin_memory()
+    for _ in range(3):                                   # a race does not show every time
+        oh = {p: torch.zeros((9, 150, 230), dtype=torch.float32).pin_memory() for p in planes}
+        g.run_host(xh, capi.G2_MASK_FULL, oh)
+        for p in planes:
+            assert torch.equal(oh[p], dev[capi.G2_PLANE_NAMES[p]].cpu()), capi.G2_PLANE_NAMES[p]
+
+
 def test_generic_width_band_equals_whole():
     H, W = 150, 170
     img = synth(3960, H, W)

@@ -111,3 +111,26 @@ def test_cvsteer_run_cli(fish_fixture, tmp_path):
         for j, suffix in enumerate(("edges", "lines_dark", "lines_bright")):
             _assert_u8_close(_read_pgm(out / f"{k}_{suffix}.pgm"), want[j], f"{k}_{suffix}")
     assert "Usage" in subprocess.run([CLI, "--help"], capture_output=True, text=True).stdout
+
+
+def test_lines_u8_every_device_of_one_process(fish_fixture):
+    """One process driving several GPUs (what cvsteer-run does: worker w -> device w % ndev).  The 8-bit TMA kernel asks
+    for more than 48 KB of dynamic shared memory, a per-DEVICE function attribute: it must be set on each GPU, not once
+    per process.  On a single-GPU box this still exercises the per-device bookkeeping on device 0."""
+    lib = capi.lib()
+    fish = fish_fixture["fish"]
+    batch = np.stack([fish, fish[::-1].copy()])
+    want = None
+    for dev in range(torch.cuda.device_count()):
+        h = C.c_void_p()
+        capi.check(lib.cvs_g2_create(C.byref(h), dev, 4, 0.67))
+        got = _lines(h, batch, 0.0)
+        lib.cvs_g2_destroy(h)
+        if want is None:
+            want = got
+            ref_maps = _oracle_maps(batch[1])
+            for k, name in enumerate(("edges", "dark", "bright")):
+                _assert_u8_close(got[k][1], ref_maps[k], name)
+        else:
+            for k in range(3):
+                assert np.array_equal(got[k], want[k]), f"device {dev} differs from device 0 (plane {k})"
