@@ -33,6 +33,7 @@ G2_MASK_STATE = 0x00000FFF
 G2_MASK_ORIENT = bit(THETA) | bit(STRENGTH) | bit(E)
 G2_MASK_FULL = G2_MASK_ORIENT | bit(G2T) | bit(H2T) | bit(MAG) | bit(PHASE)
 G2_MASK_LINES = bit(EDGES) | bit(DARK) | bit(BRIGHT)
+G2_MASK_STEER5 = bit(G2T) | bit(H2T) | bit(E) | bit(MAG) | bit(PHASE)
 G4_MASK_BASIS = 0x000007FF
 G4_MASK_STEER = bit(G4T) | bit(H4T) | bit(MAG4) | bit(PHASE4)
 STEER_DOMINANT, STEER_SCALAR, STEER_MAP = 0, 1, 2

@@ -1099,8 +1099,10 @@ extern "C" int cvs_bench_ffma(int device, int form, int iters, double* instr_per
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaFree(sink);
-    // 4 x 16 FMA instructions per iteration per thread; the packed forms (3, 4) do two lane-FMAs per instruction
-    const double n = (double)blocks * threads * (double)iters * 64.0 * ((form == 3 || form == 4) ? 2.0 : 1.0);
+    // 64 FMA instructions per `iters` unit per thread (the scalar forms run them 512 to a loop trip: iters rounds up to a
+    // multiple of 8); the packed forms (3, 4) do two lane-FMAs per instruction
+    const double units = form <= 2 ? (double)((iters + 7) / 8 * 8) : (double)iters;
+    const double n = (double)blocks * threads * units * 64.0 * ((form == 3 || form == 4) ? 2.0 : 1.0);
     *instr_per_s = n / (ms * 1e-3);
     if (elapsed_ms) *elapsed_ms = ms;
     return CVS_OK;

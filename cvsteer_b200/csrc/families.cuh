@@ -48,20 +48,21 @@ struct G2Fam {
     static constexpr int kBakedWidth = CVS_BAKED_G2_WIDTH;
     __host__ __device__ static constexpr float baked(int set, int i) { constexpr float t[NSETS][R + 1] = CVS_BAKED_G2_TAPS; return t[set][i]; }
 
-    // does this launch read the per-pixel steering-angle map?  (static masks always steer at the in-kernel theta_d)
+    // does this launch read the per-pixel steering-angle map?
     template <unsigned MASK>
     __device__ __forceinline__ static bool reads_theta_map(const MarchArgs& a)
     {
-        return MASK == 0 && a.steer_source == CVS_STEER_MAP && (a.mask & (kNeedsSteer | CVS_BIT(CVS_E)));
+        if (MASK) return (MASK >> MARCH_SRC_SHIFT) == CVS_STEER_MAP && (MASK & (kNeedsSteer | CVS_BIT(CVS_E)));
+        return a.steer_source == CVS_STEER_MAP && (a.mask & (kNeedsSteer | CVS_BIT(CVS_E)));
     }
 
     static constexpr unsigned kNeedsOrient = 0x000FFF80u;   // anything beyond the 7 basis planes
     static constexpr unsigned kNeedsSteer = CVS_BIT(CVS_G2T) | CVS_BIT(CVS_H2T) | CVS_BIT(CVS_MAG) | CVS_BIT(CVS_PHASE) |
                                             CVS_BIT(CVS_EDGES) | CVS_BIT(CVS_DARK) | CVS_BIT(CVS_BRIGHT);
 
-    // Fused epilogue on the 7 basis values of one pixel.  MASK != 0: compile-time plane set, steering at the
-    // in-kernel dominant angle, SFU approximations for 1/x, sqrt and sin/cos (all far inside the 1e-4-of-range /
-    // 1e-3 rad parity budget).  MASK == 0: run-time mask and steer source, accurate sincosf for arbitrary angles.
+    // Fused epilogue on the 7 basis values of one pixel.  MASK != 0: compile-time plane set and steering source (see
+    // march_key), SFU approximations for 1/x, sqrt and sin/cos (all far inside the 1e-4-of-range / 1e-3 rad parity
+    // budget).  MASK == 0: run-time mask and steer source, accurate sincosf for arbitrary angles.
     // Nothing in here diverges: there is no bounds predicate (out-of-range threads are clamped onto a valid column).
     template <unsigned MASK, class Cursor>
     __device__ __forceinline__ static void epilogue(const float (&b)[NBASIS], const MarchArgs& a, const Cursor& cur, float theta_px)
@@ -69,14 +70,14 @@ struct G2Fam {
         // The class state (M0: what setup() leaves behind and the getters return) takes the exact cv::cartToPolar sequence
         // (IEEE division and sqrt, NaNs propagate): that kernel is HBM-bound, the extra ~20 instructions are free.
         constexpr bool FAST = MASK != 0 && MASK != CVS_G2_MASK_STATE;
-        const unsigned m = MASK ? MASK : a.mask;
+        const unsigned m = MASK ? (MASK & MARCH_PLANE_BITS) : a.mask;
         auto put = [&](int p, float v) { cur.put(a, p, v); };
 #pragma unroll
         for (int q = 0; q < NBASIS; ++q)
             if (m & (1u << q)) put(q, b[q]);
         if (!(m & kNeedsOrient)) return;
 
-        const int src = MASK ? (int)CVS_STEER_DOMINANT : a.steer_source;
+        const int src = MASK ? (int)(MASK >> MARCH_SRC_SHIFT) : a.steer_source;
         dev::Orientation o{};
         const bool need_orient = (m & (CVS_BIT(CVS_C1) | CVS_BIT(CVS_C2) | CVS_BIT(CVS_C3) | CVS_BIT(CVS_THETA) |
                                        CVS_BIT(CVS_STRENGTH) | CVS_BIT(CVS_E))) || src == CVS_STEER_DOMINANT;
@@ -101,6 +102,8 @@ struct G2Fam {
             if (src == CVS_STEER_SCALAR) {
                 ct = a.cos_t;
                 st = a.sin_t;
+            } else if (FAST) {
+                __sincosf(theta_px, &st, &ct);  // MUFU works on theta / 2 pi mod 1: abs error < 5e-7 (+ 6e-8 |theta| beyond pi)
             } else {
                 dev::sincos_steer(theta_px, &st, &ct);
             }
@@ -128,8 +131,9 @@ struct G2Fam {
 #ifndef CVS_G4_BH
 #define CVS_G4_BH 64
 #endif
+// 3 CTAs (12 warps) per SM: the pipelined loop with its 2R-slot window needs 144-156 registers (round 1: 167 with MIN_CTAS 2)
 #ifndef CVS_G4_MIN_CTAS
-#define CVS_G4_MIN_CTAS 2
+#define CVS_G4_MIN_CTAS 3
 #endif
 struct G4Fam {
     static constexpr int R = 6, NSETS = 11, NROW = 9, NBASIS = 11, NPLANES = CVS_G4_NPLANES, BH = CVS_G4_BH, MIN_CTAS = CVS_G4_MIN_CTAS;
@@ -184,26 +188,27 @@ struct G4Fam {
         else r.theta = 0.5f * dev::wrap_pi(dev::cv_atan2<false, true>(c[2], c[1]));
         return r;
     }
-    // static steer masks are only dispatched for map steering (march_g4.cu)
     template <unsigned MASK>
     __device__ __forceinline__ static bool reads_theta_map(const MarchArgs& a)
     {
-        return MASK ? (MASK & kNeedsSteer) != 0 : (a.steer_source == CVS_STEER_MAP && (a.mask & kNeedsSteer));
+        if (MASK) return (MASK >> MARCH_SRC_SHIFT) == CVS_STEER_MAP && (MASK & kNeedsSteer) != 0;
+        return a.steer_source == CVS_STEER_MAP && (a.mask & kNeedsSteer);
     }
 
-    // MASK != 0: compile-time plane set, steering at a per-pixel angle map (config 4), SFU approximations.
-    // MASK == 0: run-time mask; steering at a scalar angle, an angle map, or the in-kernel dominant angle.
+    // MASK != 0: compile-time plane set and steering source (march_key; config 4 = steer mask at a per-pixel angle map),
+    // SFU approximations.  MASK == 0: run-time mask; steering at a scalar angle, an angle map, or the in-kernel dominant angle.
     template <unsigned MASK, class Cursor>
     __device__ __forceinline__ static void epilogue(const float (&b)[NBASIS], const MarchArgs& a, const Cursor& cur, float theta_px)
     {
         constexpr bool FAST = MASK != 0;
-        const unsigned m = MASK ? MASK : a.mask;
+        const unsigned m = MASK ? (MASK & MARCH_PLANE_BITS) : a.mask;
+        const int src = MASK ? (int)(MASK >> MARCH_SRC_SHIFT) : a.steer_source;
         auto put = [&](int p, float v) { cur.put(a, p, v); };
 #pragma unroll
         for (int q = 0; q < NBASIS; ++q)
             if (m & (1u << q)) put(q, b[q]);
         if (!(m & (kNeedsSteer | kNeedsOrient))) return;
-        const bool dominant = !MASK && a.steer_source == CVS_STEER_DOMINANT;
+        const bool dominant = src == CVS_STEER_DOMINANT;
         if ((m & kNeedsOrient) || (dominant && (m & kNeedsSteer))) {
             const dev::Orientation o = orientation<FAST>(b);
             if (m & CVS_BIT(CVS_G4_THETA)) put(CVS_G4_THETA, o.theta);
@@ -212,9 +217,13 @@ struct G4Fam {
         }
         if (!(m & kNeedsSteer)) return;
         float ct, st;
-        if (!MASK && a.steer_source == CVS_STEER_SCALAR) {
+        if (src == CVS_STEER_SCALAR) {
             ct = a.cos_t;
             st = a.sin_t;
+        } else if (FAST) {
+            // MUFU.SIN/COS work on theta / 2 pi modulo 1: no range branch, abs error < 5e-7 for |theta| <= pi and
+            // ~6e-8 * |theta| beyond (the fp32 rounding of theta / 2 pi) -- 1e-6 of the basis range after steering
+            __sincosf(theta_px, &st, &ct);
         } else {
             dev::sincos_steer(theta_px, &st, &ct);
         }

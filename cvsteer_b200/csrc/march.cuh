@@ -47,6 +47,13 @@
 #ifndef CVS_MARCH_SHIFT_U
 #define CVS_MARCH_SHIFT_U 4
 #endif
+// Static-mask kernels of families WITH a shared row pass (G4: 13 slot bodies) run a software-pipelined loop: the row pass of
+// tile row rt+1 is issued in the same basic block as the point-wise epilogue of output row rt, so its 59 independent FMAs
+// and 13 shared-memory loads fill the issue slots the epilogue's long dependent chain (sincos -> weights -> steer ->
+// rcp -> atan polynomial) leaves empty at 3 warps per scheduler.  0 = the plain rolled loop.
+#ifndef CVS_MARCH_PIPE
+#define CVS_MARCH_PIPE 1
+#endif
 #ifndef CVS_CURSOR_MAX_PLANES
 #define CVS_CURSOR_MAX_PLANES 8
 #endif
@@ -91,6 +98,11 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
         ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
         : "memory");
 }
+// contiguous bytes -> L2 (no shared-memory destination, no completion to wait for); 16-byte aligned address and size
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map)
 {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -101,6 +113,10 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map)
 // Kernel arguments
 // ------------------------------------------------------------------------------------------------
 enum { MARCH_TW = 128, MARCH_MAX_OUT = 20 };
+// Static specialisations are keyed by the plane mask AND the steering source: key = planes | source << 28 (source 0 =
+// the in-kernel dominant angle, so a bare plane mask keeps meaning "steer at theta_d").  Key 0 = everything at run time.
+enum : unsigned { MARCH_PLANE_BITS = 0x0FFFFFFFu, MARCH_SRC_SHIFT = 28 };
+__host__ __device__ constexpr unsigned march_key(unsigned planes, int steer_source) { return planes | ((unsigned)steer_source << MARCH_SRC_SHIFT); }
 // TMA needs every box row to START on a 16-byte boundary of global memory, i.e. the innermost start coordinate must be
 // a multiple of 4 floats (x0 - 6 faults with "illegal instruction"; x0 - 4 and x0 - 8 are fine).  So the tile's left
 // halo is the radius rounded up to 4 floats, and the row pitch follows.
@@ -181,7 +197,9 @@ struct OutCursor {
 #pragma unroll
         for (int q = 0; q < NPLANES; ++q)
             base[q] = (MASK >> q & 1u) ? opaque64((unsigned long long)(reinterpret_cast<char*>(a.out[q]) + band_off)) : 0ull;
-        th_base = opaque64((unsigned long long)(reinterpret_cast<const char*>(a.theta_map) + band_off));
+        th_base = (MASK >> MARCH_SRC_SHIFT) == 2u /* CVS_STEER_MAP */
+                      ? opaque64((unsigned long long)(reinterpret_cast<const char*>(a.theta_map) + band_off))
+                      : 0ull;
         idx = (unsigned)x;
         pitch_elems = (unsigned)(a.out_pitch >> 2);
     }
@@ -428,6 +446,21 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
         load_tile_manual<R, TWH, TROWS, TIn>(tile, a, frame, x0, ytop, NT);
     }
 
+    // Steering-angle map of this CTA's band -> L2, one 512-byte row segment per thread, issued before the march starts.
+    // The in-loop load (one row ahead) then costs an L2 hit instead of a DRAM round trip: with one 128-byte line in flight
+    // per warp and 12 warps per SM, Little's law capped the map read at ~290 GB/s -- exactly what the G4 steer kernel
+    // needed, and 11 % of its warp samples sat on that load (profiles/r02_ncu_g4_steer_before.txt).
+    if constexpr (MASK != 0) {
+        if (Fam::template reads_theta_map<MASK>(a)) {
+            const int rows_here = min(BH, a.out_row_end - yb);
+            const int seg = (min(TW, a.cols - x0) * 4) & ~15;
+            const char* tp = reinterpret_cast<const char*>(a.theta_map) + (long long)frame * a.out_frame_stride +
+                             (long long)(yb - a.out_row_origin) * a.out_pitch + 4ll * x0;
+            if (seg > 0 && ((reinterpret_cast<uintptr_t>(tp) | (uintptr_t)a.out_pitch) & 15) == 0)
+                for (int r = threadIdx.x; r < rows_here; r += NT) ptx::bulk_prefetch_l2(tp + (long long)r * a.out_pitch, (uint32_t)seg);
+        }
+    }
+
     // Threads past the right image edge (ragged last strip) are clamped onto the last valid column: they redo that pixel
     // and store the same value to the same address, so the loop needs no bounds predicate at all.
     // (PX = 2: cols is even, host-checked, so the clamped pair stays aligned)
@@ -529,7 +562,8 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
     // Output addressing: see OutCursor.
     const long long band_off = (long long)frame * a.out_frame_stride + (long long)(yb - a.out_row_origin) * a.out_pitch;
     // per-plane base registers only pay off while there are few planes (2 registers each); wide masks share one offset
-    using Cursor = OutCursor<(__builtin_popcount(MASK) <= CVS_CURSOR_MAX_PLANES ? MASK : 0u), Fam::NPLANES>;
+    // (the same goes for the families whose nine 13-row windows leave no registers to spare: G4)
+    using Cursor = OutCursor<((__builtin_popcount(MASK & MARCH_PLANE_BITS) <= CVS_CURSOR_MAX_PLANES && !Fam::SHARED_ROW_PASS) ? MASK : 0u), Fam::NPLANES>;
     Cursor cur(a, band_off, x);
     // point-wise epilogue of the row just finished by col_pass (+ the stores), then on to the next output row
     auto emit_row = [&](float th) {
@@ -635,7 +669,61 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
             }
         }
     }
-    if constexpr (!SHIFT) {
+    constexpr bool PIPE = CVS_MARCH_PIPE && Fam::SHARED_ROW_PASS && MASK != 0 && PX == 1 && !SHIFT;
+    if constexpr (PIPE) {
+        // 2R-slot window: when the newest row arrives in r[], the rows at offsets -R .. R-1 sit in slots
+        // (slot + R + k) mod 2R and the oldest one (k = -R, slot `slot`) is replaced by r[] after the column passes --
+        // one row of registers (NROW) and one slot body less than the K-slot window of the other loops.
+        constexpr int W = 2 * R;
+        float pw[NROW][W];
+        auto col_pipe = [&](bool emit, auto slot_c) {
+            constexpr int slot = decltype(slot_c)::value;
+            if (emit) {
+#pragma unroll
+                for (int q = 0; q < NB; ++q) {
+                    const int rp = Fam::basis_row(q), set = Fam::basis_set(q);
+                    auto w = [&](int k) -> float { return k == R ? r[rp][0] : pw[rp][(slot + R + k) % W]; };
+                    float acc;
+                    if (Fam::basis_odd(q)) {
+                        acc = tap(set, 1) * (w(1) - w(-1));
+#pragma unroll
+                        for (int i = 2; i <= R; ++i) acc = fmaf(tap(set, i), w(i) - w(-i), acc);
+                    } else {
+                        acc = tap(set, 0) * w(0);
+#pragma unroll
+                        for (int i = 1; i <= R; ++i) acc = fmaf(tap(set, i), w(i) + w(-i), acc);
+                    }
+                    b[0][q] = acc;
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < NROW; ++p) pw[p][slot] = r[p][0];
+        };
+        const int total = nrows + 2 * R;  // tile rows to consume; >= 2R + 1
+        const bool maps = Fam::template reads_theta_map<MASK>(a);
+        // window-filling rows, straight-line (slots are compile-time constants: no dispatch, nothing to emit)
+        [&]<int... I>(std::integer_sequence<int, I...>) {
+            ((row_pass(I), col_pipe(false, std::integral_constant<int, I>{})), ...);
+        }(std::make_integer_sequence<int, W>{});
+        int slot = 0;
+        float th = maps ? cur.theta(a) : 0.f;
+        row_pass(W);
+#pragma unroll 1
+        for (int rt = W; rt < total; ++rt) {
+            const bool more = rt + 1 < total;  // CTA-uniform
+            // the angle of the NEXT output row (an L2 hit after the prefetch above), in flight during this row's arithmetic
+            const float th_next = maps ? cur.theta(a, more ? 1 : 0) : 0.f;
+            dispatch_tree<0, W>(slot, [&](auto slot_c) { col_pipe(true, slot_c); });
+            slot = (slot + 1 == W) ? 0 : slot + 1;
+            // one basic block: epilogue of this output row + row pass of the next tile row (the last iteration recomputes
+            // the final row instead of branching around it)
+            emit_row(th);
+            row_pass(more ? rt + 1 : rt);
+            th = th_next;
+        }
+        rt_done = total;
+    }
+    if constexpr (!SHIFT && !PIPE) {
     int slot = 0;  // rt_done is a multiple of K, so the window slot of tile row rt_done is 0 again
     float theta_next = 0.f;
     if (Fam::template reads_theta_map<MASK>(a) && rt_done >= 2 * R && rt_done < nrows + 2 * R) theta_next = cur.theta(a);
@@ -670,7 +758,7 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
         slot = (slot + 1 == K) ? 0 : slot + 1;
         if (rt >= 2 * R) emit_row(theta_px);
     }
-    }  // !SHIFT
+    }  // !SHIFT && !PIPE
     if (a.pyr_out) emit_next_level<R, BH, NT>(tile, a, frame, x0, yb);  // CTA-uniform; the tile is read-only after staging
 }
 

@@ -7,7 +7,7 @@ namespace cvs {
 cudaError_t launch_march_g2_lines(const BatchGeom& g, const MarchArgs& a, const TapTable<G2Fam::NSETS, G2Fam::R>& tt, dim3 grid, cudaStream_t stream,
                                   LaunchInfo* info)
 {
-    return launch_march_mask<G2Fam, CVS_G2_MASK_LINES, true>(g, a, tt, grid, stream, info, "g2_march<lines>");
+    return launch_march_mask<G2Fam, CVS_G2_MASK_LINES, true, (CVS_MARCH_PX2 > 0)>(g, a, tt, grid, stream, info, "g2_march<lines>");
 }
 
 }  // namespace cvs

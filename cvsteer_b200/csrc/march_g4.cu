@@ -5,13 +5,14 @@ namespace cvs {
 
 cudaError_t launch_march_g4(const FamilyTaps& taps, const BatchGeom& g, const MarchArgs& a, bool dom, cudaStream_t stream, LaunchInfo* info)
 {
-    (void)dom;  // dominant-angle steering runs in the run-time-mask kernel (orientation analysis in the epilogue)
+    (void)dom;  // dominant-angle steering (this library's G4 extension) runs in the run-time-mask kernel
     TapTable<G4Fam::NSETS, G4Fam::R> tt;
     fill_tap_table<G4Fam>(taps, tt);
     const int out_rows = g.out_row_end - g.out_row_begin;
     const dim3 grid((g.cols + MARCH_TW - 1) / MARCH_TW, (out_rows + G4Fam::BH - 1) / G4Fam::BH, g.n);
     const bool map = a.steer_source == CVS_STEER_MAP;
-    if (map && a.mask == CVS_G4_MASK_STEER) return launch_march_mask<G4Fam, CVS_G4_MASK_STEER, true>(g, a, tt, grid, stream, info, "g4_march<steer>");
+    if (map && a.mask == CVS_G4_MASK_STEER)
+        return launch_march_mask<G4Fam, march_key(CVS_G4_MASK_STEER, CVS_STEER_MAP), true>(g, a, tt, grid, stream, info, "g4_march<steer@map>");
     if (a.mask == CVS_G4_MASK_BASIS) return launch_march_mask<G4Fam, CVS_G4_MASK_BASIS, true>(g, a, tt, grid, stream, info, "g4_march<basis>");
     return launch_march_mask<G4Fam, 0u>(g, a, tt, grid, stream, info, "g4_march<dyn>");
 }

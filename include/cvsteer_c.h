@@ -67,6 +67,9 @@ typedef enum cvs_g2_plane {
 #define CVS_G2_MASK_ORIENT (CVS_BIT(CVS_THETA) | CVS_BIT(CVS_STRENGTH) | CVS_BIT(CVS_E))
 /* M2: full fused basis+steer+orientation: theta_d, strength, g2, h2, e, magnitude, phase */
 #define CVS_G2_MASK_FULL (CVS_G2_MASK_ORIENT | CVS_BIT(CVS_G2T) | CVS_BIT(CVS_H2T) | CVS_BIT(CVS_MAG) | CVS_BIT(CVS_PHASE))
+/* the five outputs of steer(theta, g2, h2, e, magnitude, phase) (G2.cpp:157-177) at a GIVEN angle: with CVS_STEER_SCALAR or
+ * CVS_STEER_MAP this mask has its own fused specialisation, like the masks above have for CVS_STEER_DOMINANT */
+#define CVS_G2_MASK_STEER5 (CVS_BIT(CVS_G2T) | CVS_BIT(CVS_H2T) | CVS_BIT(CVS_E) | CVS_BIT(CVS_MAG) | CVS_BIT(CVS_PHASE))
 /* the cvsteer-run per-file outputs (example/steer.cpp:88-90): findEdges / findDarkLines / findBrightLines at theta_d */
 #define CVS_G2_MASK_LINES (CVS_BIT(CVS_EDGES) | CVS_BIT(CVS_DARK) | CVS_BIT(CVS_BRIGHT))
 
