@@ -37,6 +37,7 @@ G2_MASK_STEER5 = bit(G2T) | bit(H2T) | bit(E) | bit(MAG) | bit(PHASE)
 G4_MASK_BASIS = 0x000007FF
 G4_MASK_STEER = bit(G4T) | bit(H4T) | bit(MAG4) | bit(PHASE4)
 STEER_DOMINANT, STEER_SCALAR, STEER_MAP = 0, 1, 2
+GATHER_NONE, GATHER_NCCL, GATHER_PEER_STORE, GATHER_PEER_COPY = 0, 1, 2, 3
 
 OK, ERR_INVALID_ARG, ERR_CUDA, ERR_NOT_SETUP, ERR_SIZE_MISMATCH, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 
@@ -110,6 +111,27 @@ _SIGS = {
     "cvs_g2_run_bands_host_multi": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_int,
                                               C.c_size_t, C.c_int, C.c_uint, C.POINTER(C.POINTER(C.c_void_p)),
                                               C.POINTER(C.c_size_t)]),
+    "cvs_bands_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint,
+                                   C.c_int, C.c_float]),
+    "cvs_bands_destroy": (C.c_int, [C.c_void_p]),
+    "cvs_bands_geometry": (C.c_int, [C.c_void_p, C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 6 + [C.POINTER(C.c_size_t)]),
+    "cvs_bands_input_dev": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "cvs_bands_upload_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "cvs_bands_root_bytes": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t)]),
+    "cvs_bands_root_export": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "cvs_bands_root_import": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "cvs_bands_root_attach": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cvs_bands_root_attach_planes": (C.c_int, [C.c_void_p, C.POINTER(C.POINTER(C.c_void_p)), C.POINTER(C.c_size_t)]),
+    "cvs_bands_root_plane": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "cvs_bands_local_plane": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "cvs_nccl_unique_id": (C.c_int, [C.c_char_p]),
+    "cvs_bands_nccl_init": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "cvs_bands_nccl_attach": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cvs_bands_run": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "cvs_bands_barrier": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cvs_g2_run_bands_dev_multi": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_int,
+                                             C.c_size_t, C.c_int, C.c_uint, C.c_int, C.POINTER(C.POINTER(C.c_void_p)),
+                                             C.POINTER(C.c_size_t)]),
     "cvs_bench_ffma": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), _fp]),
     "cvs_g2_last_launch": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                      C.c_char_p, C.c_int]),

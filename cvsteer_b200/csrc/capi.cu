@@ -15,10 +15,12 @@
 #include <vector>
 
 #include "../../include/cvsteer_c.h"
+#include "internal.h"
 #include "launch.h"
 #include "taps.h"
 
 using namespace cvs;
+using namespace cvsi;
 
 #define MARCH_MAX_OUT_HOST 32
 
@@ -27,7 +29,7 @@ using namespace cvs;
 // ------------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
 
-static int fail(int code, const char* fmt, ...)
+int cvsi::fail(int code, const char* fmt, ...)
 {
     va_list ap;
     va_start(ap, fmt);
@@ -35,12 +37,7 @@ static int fail(int code, const char* fmt, ...)
     va_end(ap);
     return code;
 }
-
-#define CU_TRY(expr)                                                                                         \
-    do {                                                                                                     \
-        cudaError_t e__ = (expr);                                                                            \
-        if (e__ != cudaSuccess) return fail(CVS_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
-    } while (0)
+using cvsi::fail;
 
 extern "C" const char* cvs_version(void) { return "cvsteer_b200 0.1.0 (sm_100a)"; }
 extern "C" const char* cvs_last_error(void) { return g_err; }
@@ -128,57 +125,8 @@ extern "C" int cvs_g4_make_taps(int which, int width, float spacing, float* dst)
 // ------------------------------------------------------------------------------------------------
 // handle
 // ------------------------------------------------------------------------------------------------
-namespace {
+namespace cvsi {
 
-struct DevBuf {  // owning device allocation that only ever grows; freed on release() or destruction
-    void* p = nullptr;
-    size_t bytes = 0;
-    DevBuf() = default;
-    DevBuf(const DevBuf&) = delete;
-    DevBuf& operator=(const DevBuf&) = delete;
-    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr, o.bytes = 0; }
-    ~DevBuf() { release(); }
-    cudaError_t reserve(size_t n)
-    {
-        if (n <= bytes) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr;
-        bytes = 0;
-        cudaError_t e = cudaMalloc(&p, n);
-        if (e == cudaSuccess) bytes = n;
-        return e;
-    }
-    void release()
-    {
-        if (p) cudaFree(p);
-        p = nullptr;
-        bytes = 0;
-    }
-};
-
-inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-
-struct Filter {
-    int family;  // 2 or 4
-    int device;
-    FamilyTaps taps;
-    cudaStream_t stream = nullptr;
-    cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};  // H2D / kernel / D2H pipeline of the host-batch call (lazy)
-    // resident class state of the last setup()
-    int rows = 0, cols = 0;
-    size_t pitch = 0;         // bytes, multiple of 128 (TMA needs 16)
-    DevBuf in, state, work, scratch;
-    cudaStream_t scratch_stream[3] = {nullptr, nullptr, nullptr};  // last stream that used each slice of `scratch` (generic widths)
-    bool scratch_used[3] = {false, false, false};
-    cudaEvent_t scratch_ev = nullptr;
-    int nstate = 0;           // planes in `state`: G2 12 (7 basis, c1..c3, theta, strength); G4 11
-    bool ready = false;
-    bool g4_orient_ready = false;  // planes 11, 12 of a G4 handle hold theta_d / strength of the current image
-    LaunchInfo last{};
-
-    float* state_plane(int i) const { return reinterpret_cast<float*>(static_cast<char*>(state.p) + (size_t)i * pitch * rows); }
-    float* work_plane(int i) const { return reinterpret_cast<float*>(static_cast<char*>(work.p) + (size_t)i * pitch * rows); }
-};
 
 int filter_create(Filter** out, int family, int device, int width, float spacing)
 {
@@ -304,8 +252,7 @@ int check_band(const BatchGeom& g, int radius, int full_rows_out_level, int stri
 
 // `slot` of `nslots`: callers that keep several launches in flight on different streams (the host-batch pipelines) give
 // each stream its own slice of the generic-width scratch; the per-frame scratch size does not depend on the chunk.
-int run_fused(Filter* f, const BatchGeom& g, unsigned mask, const SteerSpec& st, float* const* outs, cudaStream_t stream, int slot = 0,
-              int nslots = 1)
+int run_fused(Filter* f, const BatchGeom& g, unsigned mask, const SteerSpec& st, float* const* outs, cudaStream_t stream, int slot, int nslots)
 {
     CU_TRY(cudaSetDevice(f->device));
     float* scratch = nullptr;
@@ -451,7 +398,7 @@ int filter_steer(Filter* f, int source, float theta, const float* theta_host, si
     return CVS_OK;
 }
 
-}  // namespace
+}  // namespace cvsi
 
 // cvs_g2 / cvs_g4 are opaque to callers; both are a Filter underneath.
 
@@ -919,12 +866,7 @@ extern "C" int cvs_g2_run_batch_host_multi(int n_devices, const int* devices, in
 }
 
 // ---- row bands of one very large image over several GPUs of this process -------------------------------------------
-namespace {
-struct BandPlanC {
-    std::vector<int> rows;                       // image height per level
-    std::vector<std::pair<int, int>> out, have;  // [lo, hi) per level: rows produced / rows that must be resident
-    bool empty() const { return out[0].first >= out[0].second; }
-};
+namespace cvsi {
 
 // Same rule as cvsteer_b200/multi.py::plan_bands: band edges on multiples of 2^(levels-1) rows, so that the even-sample
 // pyramid of a band coincides with the pyramid of the whole image; `have` adds the filter halo and the pyr_down support.
@@ -1033,7 +975,7 @@ int run_band_on_device(int device, int width, float spacing, const BandPlanC& pl
     stage.release();
     return done(rc);
 }
-}  // namespace
+}  // namespace cvsi
 
 extern "C" int cvs_plan_bands(int rows, int world, int levels, int radius, int* plan, int* rows_per_level)
 {

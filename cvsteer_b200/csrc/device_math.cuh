@@ -192,6 +192,16 @@ __device__ __forceinline__ void steer_g4(float ct, float st, const float* g /*5*
                    fmaf(10.f * ct3 * st2, h[2], fmaf(-10.f * ct2 * st3, h[3], fmaf(5.f * ct * st4, h[4], -st5 * h[5])))));
 }
 
+// The same sums when the binomial factors (1 -4 6 -4 1 / 1 -5 10 -10 5 -1) are already folded into the basis values
+// (the steer-only kernels scale the column taps at compile time): 8 + 17 instructions instead of 33.
+__device__ __forceinline__ void steer_g4_prescaled(float ct, float st, const float* g /*5*/, const float* h /*6*/, float& g4, float& h4)
+{
+    const float c2 = ct * ct, s2 = st * st, cs = ct * st;
+    const float c4 = c2 * c2, c3s = c2 * cs, c2s2 = cs * cs, cs3 = cs * s2, s4 = s2 * s2;
+    g4 = fmaf(c4, g[0], fmaf(c3s, g[1], fmaf(c2s2, g[2], fmaf(cs3, g[3], s4 * g[4]))));
+    h4 = fmaf(c4 * ct, h[0], fmaf(c4 * st, h[1], fmaf(c3s * st, h[2], fmaf(c2s2 * st, h[3], fmaf(cs3 * st, h[4], (s4 * st) * h[5])))));
+}
+
 // G2.cpp:107-112
 template <bool FAST = false>
 __device__ __forceinline__ void magnitude_phase(float g, float h, float& mag, float& phase)

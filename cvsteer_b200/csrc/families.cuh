@@ -48,6 +48,11 @@ struct G2Fam {
     static constexpr int kBakedWidth = CVS_BAKED_G2_WIDTH;
     __host__ __device__ static constexpr float baked(int set, int i) { constexpr float t[NSETS][R + 1] = CVS_BAKED_G2_TAPS; return t[set][i]; }
 
+    // (no steering factors folded into the column taps for this family)
+    template <unsigned MASK, bool BAKED>
+    __host__ __device__ static constexpr bool prescaled() { return false; }
+    __host__ __device__ static constexpr float steer_coeff(int) { return 1.f; }
+
     // does this launch read the per-pixel steering-angle map?
     template <unsigned MASK>
     __device__ __forceinline__ static bool reads_theta_map(const MarchArgs& a)
@@ -64,7 +69,7 @@ struct G2Fam {
     // march_key), SFU approximations for 1/x, sqrt and sin/cos (all far inside the 1e-4-of-range / 1e-3 rad parity
     // budget).  MASK == 0: run-time mask and steer source, accurate sincosf for arbitrary angles.
     // Nothing in here diverges: there is no bounds predicate (out-of-range threads are clamped onto a valid column).
-    template <unsigned MASK, class Cursor>
+    template <unsigned MASK, bool PRESCALED = false, class Cursor>
     __device__ __forceinline__ static void epilogue(const float (&b)[NBASIS], const MarchArgs& a, const Cursor& cur, float theta_px)
     {
         // The class state (M0: what setup() leaves behind and the getters return) takes the exact cv::cartToPolar sequence
@@ -188,6 +193,18 @@ struct G4Fam {
         else r.theta = 0.5f * dev::wrap_pi(dev::cv_atan2<false, true>(c[2], c[1]));
         return r;
     }
+    // Steer-only static kernels with baked taps fold the binomial steering factors into the column taps at compile time
+    // (every basis value arrives pre-multiplied: G4 1 -4 6 -4 1, H4 1 -5 10 -10 5 -1), which shortens the epilogue by 8
+    // instructions; the scaled tap is rounded once (<= 1 ulp of the tap: 6e-8 relative).  Not when basis planes or the
+    // orientation forms are wanted as well -- those need the plain values.
+    template <unsigned MASK, bool BAKED>
+    __host__ __device__ static constexpr bool prescaled()
+    {
+        return BAKED && MASK != 0 && ((MASK & MARCH_PLANE_BITS) & (CVS_G4_MASK_BASIS | kNeedsOrient)) == 0 &&
+               (MASK >> MARCH_SRC_SHIFT) != CVS_STEER_DOMINANT;
+    }
+    __host__ __device__ static constexpr float steer_coeff(int q) { constexpr float t[11] = {1.f, -4.f, 6.f, -4.f, 1.f, 1.f, -5.f, 10.f, -10.f, 5.f, -1.f}; return t[q]; }
+
     template <unsigned MASK>
     __device__ __forceinline__ static bool reads_theta_map(const MarchArgs& a)
     {
@@ -197,7 +214,7 @@ struct G4Fam {
 
     // MASK != 0: compile-time plane set and steering source (march_key; config 4 = steer mask at a per-pixel angle map),
     // SFU approximations.  MASK == 0: run-time mask; steering at a scalar angle, an angle map, or the in-kernel dominant angle.
-    template <unsigned MASK, class Cursor>
+    template <unsigned MASK, bool PRESCALED = false, class Cursor>
     __device__ __forceinline__ static void epilogue(const float (&b)[NBASIS], const MarchArgs& a, const Cursor& cur, float theta_px)
     {
         constexpr bool FAST = MASK != 0;
@@ -228,7 +245,8 @@ struct G4Fam {
             dev::sincos_steer(theta_px, &st, &ct);
         }
         float g4, h4;
-        dev::steer_g4(ct, st, &b[0], &b[5], g4, h4);
+        if (PRESCALED) dev::steer_g4_prescaled(ct, st, &b[0], &b[5], g4, h4);
+        else dev::steer_g4(ct, st, &b[0], &b[5], g4, h4);
         if (m & CVS_BIT(CVS_G4T)) put(CVS_G4T, g4);
         if (m & CVS_BIT(CVS_H4T)) put(CVS_H4T, h4);
         if (m & (CVS_BIT(CVS_MAG4) | CVS_BIT(CVS_PHASE4))) {

@@ -476,6 +476,10 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
         else return taps.t[set][i];
     };
 
+    // column-pass tap of basis plane q: the family may fold a per-plane constant (steering factor) into it
+    constexpr bool PRESC = Fam::template prescaled<MASK, BAKED>();
+    auto ctap = [&](int q, int set, int i) -> float { return PRESC ? tap(set, i) * Fam::steer_coeff(q) : tap(set, i); };
+
     float win[NROW][K][PX];  // (2R+1)-row register window per row-filtered plane; slot indices are compile-time
     float b[PX][NB];
 
@@ -537,13 +541,13 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
                     auto w = [&](int k) -> float { return k == R ? r[rp][px] : win[rp][(slot + 1 + R + k + K) % K][px]; };
                     float acc;
                     if (Fam::basis_odd(q)) {
-                        acc = tap(set, 1) * (w(1) - w(-1));
+                        acc = ctap(q, set, 1) * (w(1) - w(-1));
 #pragma unroll
-                        for (int i = 2; i <= R; ++i) acc = fmaf(tap(set, i), w(i) - w(-i), acc);
+                        for (int i = 2; i <= R; ++i) acc = fmaf(ctap(q, set, i), w(i) - w(-i), acc);
                     } else {
-                        acc = tap(set, 0) * w(0);
+                        acc = ctap(q, set, 0) * w(0);
 #pragma unroll
-                        for (int i = 1; i <= R; ++i) acc = fmaf(tap(set, i), w(i) + w(-i), acc);
+                        for (int i = 1; i <= R; ++i) acc = fmaf(ctap(q, set, i), w(i) + w(-i), acc);
                     }
                     b[px][q] = acc;
                 }
@@ -568,10 +572,10 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
     // point-wise epilogue of the row just finished by col_pass (+ the stores), then on to the next output row
     auto emit_row = [&](float th) {
         if constexpr (PX == 1) {
-            Fam::template epilogue<MASK>(b[0], a, cur, th);
+            Fam::template epilogue<MASK, PRESC>(b[0], a, cur, th);
         } else {
-            Fam::template epilogue<MASK>(b[0], a, PairLeft<Cursor>{cur}, th);
-            Fam::template epilogue<MASK>(b[1], a, PairRight<Cursor>{cur}, th);
+            Fam::template epilogue<MASK, PRESC>(b[0], a, PairLeft<Cursor>{cur}, th);
+            Fam::template epilogue<MASK, PRESC>(b[1], a, PairRight<Cursor>{cur}, th);
         }
         cur.next_row();
     };
@@ -598,13 +602,13 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
                     auto w = [&](int k) -> float { return lw[rp][u + R + k][px]; };
                     float acc;
                     if (Fam::basis_odd(q)) {
-                        acc = tap(set, 1) * (w(1) - w(-1));
+                        acc = ctap(q, set, 1) * (w(1) - w(-1));
 #pragma unroll
-                        for (int i = 2; i <= R; ++i) acc = fmaf(tap(set, i), w(i) - w(-i), acc);
+                        for (int i = 2; i <= R; ++i) acc = fmaf(ctap(q, set, i), w(i) - w(-i), acc);
                     } else {
-                        acc = tap(set, 0) * w(0);
+                        acc = ctap(q, set, 0) * w(0);
 #pragma unroll
-                        for (int i = 1; i <= R; ++i) acc = fmaf(tap(set, i), w(i) + w(-i), acc);
+                        for (int i = 1; i <= R; ++i) acc = fmaf(ctap(q, set, i), w(i) + w(-i), acc);
                     }
                     b[px][q] = acc;
                 }
@@ -685,13 +689,13 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
                     auto w = [&](int k) -> float { return k == R ? r[rp][0] : pw[rp][(slot + R + k) % W]; };
                     float acc;
                     if (Fam::basis_odd(q)) {
-                        acc = tap(set, 1) * (w(1) - w(-1));
+                        acc = ctap(q, set, 1) * (w(1) - w(-1));
 #pragma unroll
-                        for (int i = 2; i <= R; ++i) acc = fmaf(tap(set, i), w(i) - w(-i), acc);
+                        for (int i = 2; i <= R; ++i) acc = fmaf(ctap(q, set, i), w(i) - w(-i), acc);
                     } else {
-                        acc = tap(set, 0) * w(0);
+                        acc = ctap(q, set, 0) * w(0);
 #pragma unroll
-                        for (int i = 1; i <= R; ++i) acc = fmaf(tap(set, i), w(i) + w(-i), acc);
+                        for (int i = 1; i <= R; ++i) acc = fmaf(ctap(q, set, i), w(i) + w(-i), acc);
                     }
                     b[0][q] = acc;
                 }
@@ -701,10 +705,22 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
         };
         const int total = nrows + 2 * R;  // tile rows to consume; >= 2R + 1
         const bool maps = Fam::template reads_theta_map<MASK>(a);
-        // window-filling rows, straight-line (slots are compile-time constants: no dispatch, nothing to emit)
-        [&]<int... I>(std::integer_sequence<int, I...>) {
-            ((row_pass(I), col_pipe(false, std::integral_constant<int, I>{})), ...);
-        }(std::make_integer_sequence<int, W>{});
+        // Window-filling rows (nothing to emit): PRE rows at a time go straight-line into the LAST PRE slots, and the window is
+        // shifted down by PRE at the top of every trip, so after W / PRE trips tile row j sits in slot j.  No dispatch (a
+        // second dispatch tree made ptxas spill the window), and 4 row bodies of code instead of 12: straight-line code
+        // that runs once per CTA is always cold in the instruction cache (15 % no_instructions samples with 12 bodies).
+        constexpr int PRE = 4;
+        static_assert(W % PRE == 0, "pre-roll trips");
+#pragma unroll 1
+        for (int it = 0; it < W / PRE; ++it) {
+#pragma unroll
+            for (int p = 0; p < NROW; ++p)
+#pragma unroll
+                for (int i = 0; i < W - PRE; ++i) pw[p][i] = pw[p][i + PRE];  // (first trip: moves don't-care values)
+            [&]<int... I>(std::integer_sequence<int, I...>) {
+                ((row_pass(it * PRE + I), col_pipe(false, std::integral_constant<int, W - PRE + I>{})), ...);
+            }(std::make_integer_sequence<int, PRE>{});
+        }
         int slot = 0;
         float th = maps ? cur.theta(a) : 0.f;
         row_pass(W);

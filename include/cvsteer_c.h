@@ -261,10 +261,63 @@ CVS_API int cvs_plan_bands(int rows, int world, int levels, int radius, int* pla
  * from the host image (no halo exchange), builds its slice of the `levels`-level pyramid in band mode, runs the fused
  * kernel per level and downloads its rows directly into the caller's full-size planes outs[level][plane] (row pitch
  * out_steps[level]) -- the gather IS the download.  Bit-identical to the single-GPU whole-image pyramid.  The
- * device-resident variant (outputs gathered to a root GPU with NCCL over NVLink) is cvsteer_b200/multi.py::run_bands. */
+ * device-resident variants (outputs gathered in a root GPU's memory over NVLink) are cvs_bands_* / cvs_g2_run_bands_dev_multi below. */
 CVS_API int cvs_g2_run_bands_host_multi(int n_devices, const int* devices, int width, float spacing, const float* image,
                                         int rows, int cols, size_t step, int levels, unsigned mask,
                                         float* const* const* outs, const size_t* out_steps);
+
+/* ================================ row bands, device-resident (config 5) ================================
+ * ONE very large image split into ROW BANDS over several GPUs with the outputs gathered in the ROOT GPU's memory.  A
+ * cvs_bands context is one rank (= one GPU; one process per GPU, or one host thread per GPU) of such a run.  It owns the
+ * rank's slice of every pyramid level (band + halo, planned as cvs_plan_bands does), runs band-mode pyr_down + the fused
+ * kernel level by level, and delivers its rows to the root's full-size planes:
+ *   CVS_GATHER_NONE        results stay in this rank's local planes (cvs_bands_local_plane);
+ *   CVS_GATHER_NCCL        grouped ncclSend/ncclRecv per level on a second stream, level l travelling while level l+1 computes;
+ *   CVS_GATHER_PEER_STORE  the fused kernel stores straight into the root's planes over NVLink peer memory (compute and
+ *                          gather are ONE kernel; no local planes, no second pass);
+ *   CVS_GATHER_PEER_COPY   local planes + one copy-engine transfer per level into the root's planes, overlapped like NCCL.
+ * Bit-identical to the single-GPU whole-image pyramid in every mode.  No reference counterpart (one image, one thread:
+ * example/steer.cpp:69-124).  NCCL is bound at run time (the libnccl already loaded in the process, else the system one). */
+typedef struct cvs_bands cvs_bands;
+typedef enum cvs_band_gather { CVS_GATHER_NONE = 0, CVS_GATHER_NCCL = 1, CVS_GATHER_PEER_STORE = 2, CVS_GATHER_PEER_COPY = 3 } cvs_band_gather;
+#define CVS_NCCL_ID_BYTES 128
+
+CVS_API int cvs_bands_create(cvs_bands** out, int device, int rank, int world, int root, int rows, int cols, int levels,
+                             unsigned mask, int width, float spacing);
+CVS_API int cvs_bands_destroy(cvs_bands* b);
+/* geometry of `rank` (-1 = this context's own) at `level`: image size of the level, rows produced [out_lo, out_hi), rows held
+ * [have_lo, have_hi), row pitch (bytes) of the context's level buffers / local planes / own root planes.  Any out may be NULL. */
+CVS_API int cvs_bands_geometry(const cvs_bands* b, int rank, int level, int* level_rows, int* level_cols, int* out_lo, int* out_hi,
+                               int* have_lo, int* have_hi, size_t* pitch);
+/* level-0 input of this rank: device buffer holding image rows [have_lo, have_hi) (fill it in place), or upload from a host image */
+CVS_API int cvs_bands_input_dev(cvs_bands* b, float** ptr, size_t* pitch);
+CVS_API int cvs_bands_upload_host(cvs_bands* b, const float* image /* row 0 of the WHOLE image */, size_t step, void* stream);
+/* the root's planes: the root allocates one block (cvs_bands_root_bytes) and exports a CUDA IPC handle; other processes import
+ * it with their own GPU current; threads of the root's process attach the block pointer (after cvs_enable_peer_access) or
+ * caller-owned planes[level][plane] with per-level pitches */
+CVS_API int cvs_bands_root_bytes(const cvs_bands* b, size_t* bytes);
+CVS_API int cvs_bands_root_export(cvs_bands* b, unsigned char handle[CVS_IPC_HANDLE_BYTES], void** base);
+CVS_API int cvs_bands_root_import(cvs_bands* b, const unsigned char handle[CVS_IPC_HANDLE_BYTES]);
+CVS_API int cvs_bands_root_attach(cvs_bands* b, void* base);
+CVS_API int cvs_bands_root_attach_planes(cvs_bands* b, float* const* const* planes, const size_t* pitches);
+CVS_API int cvs_bands_root_plane(cvs_bands* b, int level, int plane, float** ptr, size_t* pitch);
+CVS_API int cvs_bands_local_plane(cvs_bands* b, int level, int plane, float** ptr, size_t* pitch);
+/* NCCL communicator over the band ranks: created here from a unique id (rank 0 makes it, the caller's control plane carries
+ * it to the others; collective), or a caller-owned ncclComm_t */
+CVS_API int cvs_nccl_unique_id(unsigned char id[CVS_NCCL_ID_BYTES]);
+CVS_API int cvs_bands_nccl_init(cvs_bands* b, const unsigned char id[CVS_NCCL_ID_BYTES]);
+CVS_API int cvs_bands_nccl_attach(cvs_bands* b, void* nccl_comm);
+/* One step (all levels), asynchronous on `stream`: when the stream has drained, this rank's kernels, copies and sends (root:
+ * receives) are complete.  With the peer modes the root additionally needs every OTHER rank's stream to have drained:
+ * cvs_bands_barrier enqueues a 1-element ncclAllReduce on the stream for that (or use your own barrier). */
+CVS_API int cvs_bands_run(cvs_bands* b, int gather, void* stream);
+CVS_API int cvs_bands_barrier(cvs_bands* b, void* stream);
+/* The same from ONE process over n_devices GPUs (a host thread per GPU, peer access to devices[0]): image in host memory,
+ * outputs device-resident in caller-owned planes root_planes[level][plane] on devices[0] (row pitch root_pitches[level]).
+ * gather = CVS_GATHER_PEER_STORE or CVS_GATHER_PEER_COPY.  Synchronous. */
+CVS_API int cvs_g2_run_bands_dev_multi(int n_devices, const int* devices, int width, float spacing, const float* image, int rows,
+                                       int cols, size_t step, int levels, unsigned mask, int gather,
+                                       float* const* const* root_planes, const size_t* root_pitches);
 
 /* ---- measurement helpers (used by bench.py; not part of the reference surface) ---- */
 /* Saturating FFMA loop: returns achieved fp32 instructions/s (1 FFMA = 1 instr = 2 flop).
