@@ -236,8 +236,9 @@ class Ctx:
         ms = self.max_over_ranks(e0.elapsed_time(e1) / steps)
         return ms, self.sampler.summary(t0, t1)
 
-    def roofline(self, px, bpp, ipp, ms, kernel=None, traffic=None, sustained=None):
-        """Both sides of the roofline for `px` pixels per launch in `ms`; the top-level keys describe the BINDING side."""
+    def roofline(self, px, bpp, ipp, ms, kernel=None, traffic=None, sustained=None, brief=True):
+        """Both sides of the roofline for `px` pixels per launch in `ms`; the top-level keys describe the BINDING side.
+        brief: leave out the prose (how each denominator was obtained) -- the headline's roofline carries it once."""
         gbs = px * bpp / 1e9 / (ms / 1e3)
         tis = px * ipp / 1e12 / (ms / 1e3)
         t_h, t_f = px * bpp / (self.hbm_peak * 1e9), px * ipp / FP32_NOMINAL
@@ -264,6 +265,10 @@ class Ctx:
             r["kernel"] = kernel
         if sustained:
             r["sustained"] = sustained
+        if brief:
+            for d in (r, hbm, fp):
+                for k in ("peak_source", "nominal_how", "measured_how"):
+                    d.pop(k, None)
         return r
 
 
@@ -308,7 +313,7 @@ def run_headline(cx, args):
                      "Mpix_s": round(cx.world * px / 1e6 / (ms_s / 1e3), 1),
                      "frac_fp32_nominal": round(px * MODES[mode]["ipp"] / (ms_s / 1e3) / FP32_NOMINAL, 3),
                      "frac_hbm_measured": round(px * MODES[mode]["bpp"] / 1e9 / (ms_s / 1e3) / cx.hbm_peak, 3), "clocks": clk_s}
-    roof = cx.roofline(px, MODES[mode]["bpp"], MODES[mode]["ipp"], ms, launch["kernel"], traffic_of(mode), sustained)
+    roof = cx.roofline(px, MODES[mode]["bpp"], MODES[mode]["ipp"], ms, launch["kernel"], traffic_of(mode), sustained, brief=False)
     cfg = {"workload": WORKLOAD, "mode": mode, "what": MODES[mode]["what"], "frames_per_gpu": FRAMES, "rows": ROWS,
            "cols": COLS, "sharding": "frames, no collective",
            "l2": "inputs (531 MB/GPU) larger than the 126 MB L2; no flush needed",

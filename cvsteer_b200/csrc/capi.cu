@@ -815,12 +815,20 @@ extern "C" int cvs_g2_lines_u8_host(cvs_g2* h, const uint8_t* gray, int n, int r
         BatchGeom g = whole_frame_geom(din, true, nf, rows, cols, pin, pin * rows, pf, pf * rows);
         float* outs[CVS_G2_NPLANES] = {nullptr};
         for (int i = 0; i < 3; ++i) outs[planes[i]] = reinterpret_cast<float*>(w + in_bytes + i * f_bytes);
+        const bool all3 = outs8[0] && outs8[1] && outs8[2];
+        // all three maps + min-max normalisation on the tuned path: the fused kernel reduces the statistics itself (one atomic
+        // pair per map per warp), so the float maps are read back once (conversion) instead of twice (min/max + conversion)
+        const bool fused_mm = all3 && !(gain > 0.f) && uses_march_path(2, f->taps.width);
+        if (fused_mm) {
+            CU_TRY(launch_minmax_init(mm, 3 * nf, s));
+            g.minmax = mm;
+            g.minmax_frames = nf;
+        }
         int rc = run_fused(f, g, mask, st, outs, s, ci % nbuf, nbuf);
         if (rc) return rc;
         uint8_t* dout0 = reinterpret_cast<uint8_t*>(w + in_bytes + 3 * f_bytes);
-        const bool all3 = outs8[0] && outs8[1] && outs8[2];
-        if (all3)  // the three maps are 3*nf consecutive frames: one min-max + one conversion launch for all of them
-            CU_TRY(launch_to_u8(outs[planes[0]], pf, pf * rows, 3 * nf, rows, cols, gain, mm, dout0, p8, p8 * rows, s));
+        if (all3)  // the three maps are 3*nf consecutive frames: one conversion launch for all of them
+            CU_TRY(launch_to_u8(outs[planes[0]], pf, pf * rows, 3 * nf, rows, cols, gain, mm, dout0, p8, p8 * rows, s, fused_mm));
         for (int i = 0; i < 3; ++i) {
             if (!outs8[i]) continue;
             uint8_t* dout = dout0 + i * o_bytes;

@@ -69,8 +69,9 @@ struct G2Fam {
     // march_key), SFU approximations for 1/x, sqrt and sin/cos (all far inside the 1e-4-of-range / 1e-3 rad parity
     // budget).  MASK == 0: run-time mask and steer source, accurate sincosf for arbitrary angles.
     // Nothing in here diverges: there is no bounds predicate (out-of-range threads are clamped onto a valid column).
-    template <unsigned MASK, bool PRESCALED = false, class Cursor>
-    __device__ __forceinline__ static void epilogue(const float (&b)[NBASIS], const MarchArgs& a, const Cursor& cur, float theta_px)
+    template <unsigned MASK, bool PRESCALED = false, bool PRECS = false, class Cursor>
+    __device__ __forceinline__ static void epilogue(const float (&b)[NBASIS], const MarchArgs& a, const Cursor& cur, float theta_px, float = 0.f,
+                                                    float = 0.f)
     {
         // The class state (M0: what setup() leaves behind and the getters return) takes the exact cv::cartToPolar sequence
         // (IEEE division and sqrt, NaNs propagate): that kernel is HBM-bound, the extra ~20 instructions are free.
@@ -126,9 +127,22 @@ struct G2Fam {
             if (m & CVS_BIT(CVS_MAG)) put(CVS_MAG, mag);
             if (m & CVS_BIT(CVS_PHASE)) put(CVS_PHASE, ph);
             // find*(magnitude, phase): both reference callers feed magnitude (example/steer.cpp:88-90)
-            if (m & CVS_BIT(CVS_EDGES)) put(CVS_EDGES, mag * dev::phase_weight<FAST>(ph, 1.57079637050628662f, false));
-            if (m & CVS_BIT(CVS_DARK)) put(CVS_DARK, mag * dev::phase_weight<FAST>(ph, 0.f, true));
-            if (m & CVS_BIT(CVS_BRIGHT)) put(CVS_BRIGHT, mag * dev::phase_weight<FAST>(ph, 3.14159274101257324f, true));
+            constexpr bool TRACK = (MASK & MARCH_MINMAX_FLAG) != 0;  // fused NORM_MINMAX statistics of the three maps
+            if (m & CVS_BIT(CVS_EDGES)) {
+                const float v = mag * dev::phase_weight<FAST>(ph, 1.57079637050628662f, false);
+                put(CVS_EDGES, v);
+                if (TRACK) cur.track(0, v);
+            }
+            if (m & CVS_BIT(CVS_DARK)) {
+                const float v = mag * dev::phase_weight<FAST>(ph, 0.f, true);
+                put(CVS_DARK, v);
+                if (TRACK) cur.track(1, v);
+            }
+            if (m & CVS_BIT(CVS_BRIGHT)) {
+                const float v = mag * dev::phase_weight<FAST>(ph, 3.14159274101257324f, true);
+                put(CVS_BRIGHT, v);
+                if (TRACK) cur.track(2, v);
+            }
         }
     }
 };
@@ -214,8 +228,11 @@ struct G4Fam {
 
     // MASK != 0: compile-time plane set and steering source (march_key; config 4 = steer mask at a per-pixel angle map),
     // SFU approximations.  MASK == 0: run-time mask; steering at a scalar angle, an angle map, or the in-kernel dominant angle.
-    template <unsigned MASK, bool PRESCALED = false, class Cursor>
-    __device__ __forceinline__ static void epilogue(const float (&b)[NBASIS], const MarchArgs& a, const Cursor& cur, float theta_px)
+    // PRECS: cos / sin of this pixel's steering angle were computed by the caller one row ahead (ct_pre, st_pre), which takes
+    // the angle load and the MUFU latency off the head of the epilogue's dependent chain.
+    template <unsigned MASK, bool PRESCALED = false, bool PRECS = false, class Cursor>
+    __device__ __forceinline__ static void epilogue(const float (&b)[NBASIS], const MarchArgs& a, const Cursor& cur, float theta_px,
+                                                    float ct_pre = 0.f, float st_pre = 0.f)
     {
         constexpr bool FAST = MASK != 0;
         const unsigned m = MASK ? (MASK & MARCH_PLANE_BITS) : a.mask;
@@ -237,6 +254,9 @@ struct G4Fam {
         if (src == CVS_STEER_SCALAR) {
             ct = a.cos_t;
             st = a.sin_t;
+        } else if (PRECS && !dominant) {
+            ct = ct_pre;
+            st = st_pre;
         } else if (FAST) {
             // MUFU.SIN/COS work on theta / 2 pi modulo 1: no range branch, abs error < 5e-7 for |theta| <= pi and
             // ~6e-8 * |theta| beyond (the fp32 rounding of theta / 2 pi) -- 1e-6 of the basis range after steering

@@ -142,6 +142,7 @@ cudaError_t launch_basis_fused(int family, const FamilyTaps& taps, const BatchGe
             if (ac.out[p]) ac.out[p] = reinterpret_cast<float*>(reinterpret_cast<char*>(a.out[p]) + (size_t)f0 * g.out_frame_stride);
         if (ac.theta_map) ac.theta_map = reinterpret_cast<const float*>(reinterpret_cast<const char*>(a.theta_map) + (size_t)f0 * g.out_frame_stride);
         if (ac.pyr_out) ac.pyr_out = reinterpret_cast<float*>(reinterpret_cast<char*>(a.pyr_out) + (size_t)f0 * g.next_frame_stride);
+        if (ac.minmax) ac.minmax = a.minmax + 2 * (size_t)f0;
         const cudaError_t e = family == 2 ? launch_march_g2(taps, gc, ac, st.source == CVS_STEER_DOMINANT, stream, info)
                                           : launch_march_g4(taps, gc, ac, st.source == CVS_STEER_DOMINANT, stream, info);
         if (e != cudaSuccess) return e;
@@ -543,11 +544,18 @@ __global__ void __launch_bounds__(256) k_to_u8(const float* src, long long pitch
     }
 }
 
+cudaError_t launch_minmax_init(unsigned* minmax, int n, cudaStream_t stream)
+{
+    k_minmax_init<<<(n + 255) / 256, 256, 0, stream>>>(minmax, n);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_to_u8(const float* src, size_t pitch, size_t frame_stride, int n, int rows, int cols, float gain, unsigned* minmax_scratch,
-                         unsigned char* dst, size_t dpitch, size_t dframe_stride, cudaStream_t stream)
+                         unsigned char* dst, size_t dpitch, size_t dframe_stride, cudaStream_t stream, bool minmax_ready)
 {
     if (n <= 0 || rows <= 0 || cols <= 0 || n > 65535 || rows > 65535) return cudaErrorInvalidValue;
-    if (!(gain > 0.f)) {
+    if (!(gain > 0.f) && !minmax_ready) {
         if (!minmax_scratch) return cudaErrorInvalidValue;
         k_minmax_init<<<(n + 255) / 256, 256, 0, stream>>>(minmax_scratch, n);
         // row-striding CTAs: about 8 per SM over the whole batch, at most one per row.  Few CTAs per frame when the batch

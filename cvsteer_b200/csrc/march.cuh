@@ -115,7 +115,8 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map)
 enum { MARCH_TW = 128, MARCH_MAX_OUT = 20 };
 // Static specialisations are keyed by the plane mask AND the steering source: key = planes | source << 28 (source 0 =
 // the in-kernel dominant angle, so a bare plane mask keeps meaning "steer at theta_d").  Key 0 = everything at run time.
-enum : unsigned { MARCH_PLANE_BITS = 0x0FFFFFFFu, MARCH_SRC_SHIFT = 28 };
+// Bit 27 of a key: also reduce min / max of the three `lines` maps per frame (fused cv::normalize NORM_MINMAX statistics).
+enum : unsigned { MARCH_PLANE_BITS = 0x07FFFFFFu, MARCH_MINMAX_FLAG = 0x08000000u, MARCH_SRC_SHIFT = 28 };
 __host__ __device__ constexpr unsigned march_key(unsigned planes, int steer_source) { return planes | ((unsigned)steer_source << MARCH_SRC_SHIFT); }
 // TMA needs every box row to START on a 16-byte boundary of global memory, i.e. the innermost start coordinate must be
 // a multiple of 4 floats (x0 - 6 faults with "illegal instruction"; x0 - 4 and x0 - 8 are fine).  So the tile's left
@@ -147,6 +148,10 @@ struct MarchArgs {
     // optional fused pyramid emission (whole frames only): next level = cv::pyrDown(input), written from the staged tile
     float* pyr_out;
     long long pyr_pitch, pyr_frame_stride;  // bytes
+    // optional fused min/max of the tracked maps (keys with MARCH_MINMAX_FLAG): ordered-uint32 pairs, map m of frame f at
+    // minmax[2 * (m * minmax_frames + f)] (min) and [.. + 1] (max); initialised to (0xffffffff, 0) by the caller
+    unsigned* minmax;
+    int minmax_frames;
 };
 
 // Tap tables passed BY VALUE as a kernel parameter: they live in the constant bank, so every FFMA takes
@@ -192,6 +197,8 @@ struct OutCursor {
     unsigned idx;                // element index of this thread's pixel relative to the bases
     unsigned pitch_elems;
     mutable float pend[NPLANES];  // two-pixel threads: the left pixel's value waits here for its neighbour (registers)
+    mutable float mn[3], mx[3];  // running min / max of up to three tracked maps (dead unless used)
+    __device__ __forceinline__ void track(int k, float v) const { mn[k] = fminf(mn[k], v), mx[k] = fmaxf(mx[k], v); }  // fmin/fmax skip NaNs
     __device__ __forceinline__ OutCursor(const MarchArgs& a, long long band_off, int x)
     {
 #pragma unroll
@@ -202,6 +209,8 @@ struct OutCursor {
                       : 0ull;
         idx = (unsigned)x;
         pitch_elems = (unsigned)(a.out_pitch >> 2);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) mn[k] = __int_as_float(0x7f800000), mx[k] = __int_as_float(0xff800000);  // +inf / -inf
     }
     // No predicate: threads past the right image edge are clamped onto the last valid column (see k_march), so they
     // recompute that pixel and store the identical value to the identical address.
@@ -232,7 +241,13 @@ template <int NPLANES>
 struct OutCursor<0u, NPLANES> {  // run-time mask: one shared byte offset, 64-bit add per plane at the store
     long long off, pitch;
     mutable float pend[NPLANES];
-    __device__ __forceinline__ OutCursor(const MarchArgs& a, long long band_off, int x) : off(band_off + 4ll * x), pitch(a.out_pitch) {}
+    mutable float mn[3], mx[3];
+    __device__ __forceinline__ void track(int k, float v) const { mn[k] = fminf(mn[k], v), mx[k] = fmaxf(mx[k], v); }
+    __device__ __forceinline__ OutCursor(const MarchArgs& a, long long band_off, int x) : off(band_off + 4ll * x), pitch(a.out_pitch)
+    {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) mn[k] = __int_as_float(0x7f800000), mx[k] = __int_as_float(0xff800000);
+    }
     __device__ __forceinline__ void put(const MarchArgs& a, int q, float v) const
     {
         __stcs(reinterpret_cast<float*>(reinterpret_cast<char*>(a.out[q]) + off), v);
@@ -254,11 +269,13 @@ template <class Cur>
 struct PairLeft {
     const Cur& c;
     __device__ __forceinline__ void put(const MarchArgs&, int q, float v) const { c.pend[q] = v; }
+    __device__ __forceinline__ void track(int k, float v) const { c.track(k, v); }
 };
 template <class Cur>
 struct PairRight {
     const Cur& c;
     __device__ __forceinline__ void put(const MarchArgs& a, int q, float v) const { c.put2(a, q, c.pend[q], v); }
+    __device__ __forceinline__ void track(int k, float v) const { c.track(k, v); }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -572,10 +589,10 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
     // point-wise epilogue of the row just finished by col_pass (+ the stores), then on to the next output row
     auto emit_row = [&](float th) {
         if constexpr (PX == 1) {
-            Fam::template epilogue<MASK, PRESC>(b[0], a, cur, th);
+            Fam::template epilogue<MASK, PRESC, false>(b[0], a, cur, th);
         } else {
-            Fam::template epilogue<MASK, PRESC>(b[0], a, PairLeft<Cursor>{cur}, th);
-            Fam::template epilogue<MASK, PRESC>(b[1], a, PairRight<Cursor>{cur}, th);
+            Fam::template epilogue<MASK, PRESC, false>(b[0], a, PairLeft<Cursor>{cur}, th);
+            Fam::template epilogue<MASK, PRESC, false>(b[1], a, PairRight<Cursor>{cur}, th);
         }
         cur.next_row();
     };
@@ -723,6 +740,10 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
         }
         int slot = 0;
         float th = maps ? cur.theta(a) : 0.f;
+        // cos / sin of the steering angle are computed ONE ROW AHEAD (static map kernels): the angle load and the MUFU latency
+        // leave the head of the epilogue's dependent chain (sincos -> weights -> 6-deep FMA chain -> rcp -> atan polynomial)
+        float ct = 1.f, st = 0.f;
+        if (maps) __sincosf(th, &st, &ct);
         row_pass(W);
 #pragma unroll 1
         for (int rt = W; rt < total; ++rt) {
@@ -733,9 +754,11 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
             slot = (slot + 1 == W) ? 0 : slot + 1;
             // one basic block: epilogue of this output row + row pass of the next tile row (the last iteration recomputes
             // the final row instead of branching around it)
-            emit_row(th);
+            Fam::template epilogue<MASK, PRESC, true>(b[0], a, cur, th, ct, st);
+            cur.next_row();
             row_pass(more ? rt + 1 : rt);
             th = th_next;
+            if (maps) __sincosf(th_next, &st, &ct);
         }
         rt_done = total;
     }
@@ -775,6 +798,35 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
         if (rt >= 2 * R) emit_row(theta_px);
     }
     }  // !SHIFT && !PIPE
+    if constexpr ((MASK & MARCH_MINMAX_FLAG) != 0) {
+        // CTA-wide min / max of the tracked maps: warp reduce on the order-preserving integer image of the floats, combine the
+        // warps through shared memory, then ONE atomic pair per map per CTA (same-address atomics serialise in L2).  NaNs
+        // never entered (fminf / fmaxf drop them), and a map without any finite value leaves the caller's (0xffffffff, 0)
+        // initial pair alone, exactly like k_minmax.
+        __shared__ unsigned s_mm[NT / 32][6];
+        auto ord = [](float f) { const unsigned u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); };
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const bool any = cur.mn[k] <= cur.mx[k];
+            const unsigned lo = __reduce_min_sync(0xffffffffu, any ? ord(cur.mn[k]) : 0xffffffffu);
+            const unsigned hi = __reduce_max_sync(0xffffffffu, any ? ord(cur.mx[k]) : 0u);
+            if ((threadIdx.x & 31) == 0) s_mm[threadIdx.x >> 5][2 * k] = lo, s_mm[threadIdx.x >> 5][2 * k + 1] = hi;
+        }
+        __syncthreads();
+        if (threadIdx.x < 6) {
+            const int k = threadIdx.x >> 1;
+            const bool is_max = threadIdx.x & 1;
+            unsigned v = s_mm[0][threadIdx.x];
+#pragma unroll
+            for (int w = 1; w < NT / 32; ++w) v = is_max ? max(v, s_mm[w][threadIdx.x]) : min(v, s_mm[w][threadIdx.x]);
+            unsigned* mm = a.minmax + 2 * ((long long)k * a.minmax_frames + frame) + (is_max ? 1 : 0);
+            if (is_max) {
+                if (v != 0u) atomicMax(mm, v);
+            } else if (v != 0xffffffffu) {
+                atomicMin(mm, v);
+            }
+        }
+    }
     if (a.pyr_out) emit_next_level<R, BH, NT>(tile, a, frame, x0, yb);  // CTA-uniform; the tile is read-only after staging
 }
 

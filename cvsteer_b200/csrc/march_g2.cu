@@ -26,6 +26,7 @@ cudaError_t launch_march_g2(const FamilyTaps& taps, const BatchGeom& g, const Ma
     if (mask == CVS_G2_MASK_STATE /* no steered plane: the source is irrelevant */) return launch_march_mask<G2Fam, CVS_G2_MASK_STATE, true>(g, a, tt, grid, stream, info, "g2_march<M0>");
     static const bool no_lines = getenv("CVS_NO_STATIC_LINES") != nullptr;  // A/B switch
     if (dom && mask == CVS_G2_MASK_LINES && !no_lines) return launch_march_g2_lines(g, a, tt, grid, stream, info);
+    if (a.minmax) return cudaErrorNotSupported;  // fused min/max statistics exist for the static `lines` kernel only
     static const bool no_steer5 = getenv("CVS_NO_STATIC_STEER5") != nullptr;  // A/B switch
     if (!dom && mask == CVS_G2_MASK_STEER5 && !no_steer5) return launch_march_g2_steer5(g, a, tt, grid, stream, info);
     if (!dom && (mask == CVS_G2_MASK_FULL || mask == CVS_G2_MASK_LINES) && !no_steer5) return launch_march_g2_given_angle(g, a, tt, grid, stream, info);

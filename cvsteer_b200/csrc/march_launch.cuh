@@ -196,6 +196,8 @@ static inline MarchArgs make_args(const BatchGeom& g, unsigned mask, const Steer
     a.pyr_out = g.next_level;
     a.pyr_pitch = (long long)g.next_pitch;
     a.pyr_frame_stride = (long long)g.next_frame_stride;
+    a.minmax = g.minmax;
+    a.minmax_frames = g.minmax_frames;
     for (int p = 0; p < nplanes && p < MARCH_MAX_OUT; ++p) a.out[p] = (mask >> p & 1u) ? outs[p] : nullptr;
     return a;
 }

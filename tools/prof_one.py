@@ -15,6 +15,7 @@ KERNELS = {
     "steer5s": (2, capi.G2_MASK_STEER5, capi.STEER_SCALAR), "steer5m": (2, capi.G2_MASK_STEER5, capi.STEER_MAP),
     "dyn": (2, capi.G2_MASK_FULL | capi.bit(capi.G2A), capi.STEER_DOMINANT),
     "g4b": (4, capi.G4_MASK_BASIS, capi.STEER_DOMINANT), "g4s": (4, capi.G4_MASK_STEER, capi.STEER_MAP),
+    "g4ss": (4, capi.G4_MASK_STEER, capi.STEER_SCALAR), "g4sd": (4, capi.G4_MASK_STEER, capi.STEER_DOMINANT),
 }
 
 
