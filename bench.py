@@ -479,7 +479,7 @@ def run_cfg5(cx, args):
     if cx.world > 1:
         gb = run.gather_bytes_to_root()
         res["gather_bytes_to_root"] = gb
-        for key, mode in (("nccl_gather", "nccl"), ("fused_peer_store", "peer")):
+        for key, mode in (("nccl_gather", "nccl"), ("fused_peer_store", "peer"), ("peer_copy", "copy")):
             try:
                 ms, clk2 = cx.timed(lambda: run.step(mode), steps, 1)
                 res[key + "_ms"] = round(ms, 3)
@@ -488,8 +488,13 @@ def run_cfg5(cx, args):
                 res[key + "_clocks"] = clk2
             except Exception as ex:   # pragma: no cover - report, do not lose the whole line
                 res[key + "_error"] = str(ex)[:300]
-        res["collective"] = ("row bands: one gather of the outputs to rank 0 -- ncclSend/ncclRecv grouped per level and "
-                             "overlapped with the next level's kernels, or peer-memory stores from the fused kernel")
+        res["collective"] = ("row bands: one gather of the outputs to rank 0 -- ncclSend/ncclRecv grouped per level and overlapped "
+                             "with the next level's kernels (nccl_gather), stores from inside the fused kernel into rank 0's planes "
+                             "over NVLink peer memory (fused_peer_store), or one copy-engine transfer per level (peer_copy); every "
+                             "figure includes the on-stream cross-rank barrier after which rank 0 may read the planes")
+        best = min((res[k + "_ms"], k) for k in ("nccl_gather", "fused_peer_store", "peer_copy") if k + "_ms" in res)
+        res["best_gather"] = best[1]
+        res["best_vs_ingress_bound"] = round(best[0] / (gb / 770e9 * 1e3), 3)
         res["nvlink_peer_GB_s_reference"] = 770.0
     run.close()
     torch.cuda.empty_cache()
@@ -505,7 +510,8 @@ def run_ours(args, rank, local_rank, world):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device: cvsteer_b200 has no CPU fallback"
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=240))
     cx = Ctx(rank, local_rank, world)
     cx.sampler.start()
     try:

@@ -156,16 +156,16 @@ class BandRun:
         return self._planes(self._lib.cvs_bands_local_plane, level, g["out_hi"] - g["out_lo"])
 
     def close(self):
+        """Collective with world > 1: every rank detaches at the same time (NCCL communicator, imported mapping), then a
+        barrier, then the contexts are destroyed (the root frees its block after its peers have unmapped it)."""
         if getattr(self, "_h", None) and self._h.value:
             torch.cuda.synchronize()
             if self.world > 1:
                 import torch.distributed as dist
-                if self.rank != self.root:          # importers unmap before the owner frees
-                    self._lib.cvs_bands_destroy(self._h)
-                    self._h = C.c_void_p()
+                with torch.cuda.device(self.device):
+                    capi.check(self._lib.cvs_bands_detach(self._h))
                 dist.barrier(self.group)
-            if self._h.value:
-                self._lib.cvs_bands_destroy(self._h)
+            self._lib.cvs_bands_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):

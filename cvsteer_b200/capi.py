@@ -114,6 +114,7 @@ _SIGS = {
     "cvs_bands_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint,
                                    C.c_int, C.c_float]),
     "cvs_bands_destroy": (C.c_int, [C.c_void_p]),
+    "cvs_bands_detach": (C.c_int, [C.c_void_p]),
     "cvs_bands_geometry": (C.c_int, [C.c_void_p, C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 6 + [C.POINTER(C.c_size_t)]),
     "cvs_bands_input_dev": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "cvs_bands_upload_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

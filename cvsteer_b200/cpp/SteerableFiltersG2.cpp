@@ -49,6 +49,11 @@ void SteerableFiltersG2::setup(const Matf& image)
     m_mirrorValid = 0;
     detail::check(cvs_g2_setup_host(m_handle, image.ptr(0), image.rows, image.cols, (size_t)image.step), "SteerableFiltersG2::setup");
     m_rows = image.rows, m_cols = image.cols;
+#ifdef CVSTEER_EAGER_HOST_MIRRORS
+    // strict drop-in for code that derives from this class and reads m_g2a ... m_theta without asking: fill every protected
+    // member right away, as the reference's setup() does (12 plane downloads per image; the default is lazy)
+    syncHostMirrors();
+#endif
 }
 
 void SteerableFiltersG2::setup8u(const unsigned char* gray, int rows, int cols, size_t step)
@@ -56,6 +61,9 @@ void SteerableFiltersG2::setup8u(const unsigned char* gray, int rows, int cols, 
     m_mirrorValid = 0;
     detail::check(cvs_g2_setup_host_u8(m_handle, gray, rows, cols, step), "SteerableFiltersG2::setup8u");
     m_rows = rows, m_cols = cols;
+#ifdef CVSTEER_EAGER_HOST_MIRRORS
+    syncHostMirrors();
+#endif
 }
 
 const Matf& SteerableFiltersG2::mirror(int plane, Matf& m) const

@@ -46,6 +46,9 @@ void SteerableFiltersG4::setup(const cv::Mat1f& image)
     for (int i = 0; i < 11; ++i) *p[i] = cv::Mat1f();  // mirrors are stale until syncHostMirrors()
     m_theta = cv::Mat1f();
     m_orientationStrength = cv::Mat1f();
+#ifdef CVSTEER_EAGER_HOST_MIRRORS
+    syncHostMirrors();  // strict drop-in for subclasses that read m_g4a ... m_h4f directly (11 plane downloads per image)
+#endif
 }
 
 void SteerableFiltersG4::syncHostMirrors() const

@@ -206,6 +206,27 @@ extern "C" int cvs_bands_create(cvs_bands** out, int device, int rank, int world
     return CVS_OK;
 }
 
+// First half of an orderly multi-process teardown, safe to call on every rank at the same time: waits for this rank's work,
+// destroys the library-owned NCCL communicator (ncclCommDestroy may wait for the peers' calls, so every rank must get here
+// without waiting on another rank first) and unmaps an imported root block.  The root's allocation stays valid until
+// cvs_bands_destroy, which the root calls after its peers have detached.
+extern "C" int cvs_bands_detach(cvs_bands* b)
+{
+    if (!b) return CVS_OK;
+    CU_TRY(cudaSetDevice(b->device));
+    CU_TRY(cudaDeviceSynchronize());
+    if (b->comm && b->comm_owned && nccl().ok) nccl().CommDestroy(b->comm);
+    b->comm = nullptr;
+    b->comm_owned = false;
+    if (b->root_block && b->root_mapped) {
+        CU_TRY(cudaIpcCloseMemHandle(b->root_block));
+        b->root_block = nullptr;
+        b->root_mapped = false;
+        b->rootp.clear();
+    }
+    return CVS_OK;
+}
+
 extern "C" int cvs_bands_destroy(cvs_bands* b)
 {
     if (!b) return CVS_OK;

@@ -285,6 +285,10 @@ typedef enum cvs_band_gather { CVS_GATHER_NONE = 0, CVS_GATHER_NCCL = 1, CVS_GAT
 CVS_API int cvs_bands_create(cvs_bands** out, int device, int rank, int world, int root, int rows, int cols, int levels,
                              unsigned mask, int width, float spacing);
 CVS_API int cvs_bands_destroy(cvs_bands* b);
+/* Orderly teardown with one process per rank: EVERY rank calls cvs_bands_detach (destroys the library-owned NCCL communicator,
+ * unmaps an imported root block; may wait for the peers' calls, so do not serialise the ranks), the caller's barrier, then
+ * cvs_bands_destroy (the root frees its block only now). */
+CVS_API int cvs_bands_detach(cvs_bands* b);
 /* geometry of `rank` (-1 = this context's own) at `level`: image size of the level, rows produced [out_lo, out_hi), rows held
  * [have_lo, have_hi), row pitch (bytes) of the context's level buffers / local planes / own root planes.  Any out may be NULL. */
 CVS_API int cvs_bands_geometry(const cvs_bands* b, int rank, int level, int* level_rows, int* level_cols, int* out_lo, int* out_hi,

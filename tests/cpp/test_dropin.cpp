@@ -27,6 +27,7 @@ struct Probe : fa::SteerableFiltersG2 {
         return m_g2a;
     }
     const cv::Mat1f& c1() { return m_c1; }
+    const cv::Mat1f& g2bRaw() { return m_g2b; }  // no sync: filled only by an eager-mirror build
     const cv::Mat1f& tapsG1() { return m_g1; }
 };
 
@@ -45,6 +46,11 @@ int main(int argc, char** argv)
         // --- test/test.cpp:84-90 verbatim (the 8-bit Mat converts to Mat1f implicitly, as in the reference)
         cv::Mat1f g2, h2, e, magnitude, phase, edges, linesDark, linesBright;
         Probe filters2(fish, 4, 0.67f);
+#ifdef CVSTEER_EAGER_HOST_MIRRORS
+        if (filters2.g2bRaw().empty() || filters2.g2bRaw().rows != rows) return 10;  // protected members filled by setup() itself
+#else
+        if (!filters2.g2bRaw().empty()) return 10;                                    // lazy by default
+#endif
         filters2.steer(filters2.getDominantOrientationAngle(), g2, h2, e, magnitude, phase);
         filters2.findEdges(magnitude, phase, edges);
         filters2.findDarkLines(magnitude, phase, linesDark);

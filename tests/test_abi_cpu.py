@@ -107,3 +107,29 @@ def test_band_contract_is_validated_before_any_cuda_call():
             assert rc != capi.ERR_INVALID_ARG, lib.cvs_last_error()          # geometry accepted (then CUDA, absent here)
         else:
             assert rc == capi.ERR_INVALID_ARG and (b"need" in lib.cvs_last_error() or b"invalid" in lib.cvs_last_error())
+
+
+def test_band_context_arguments_and_no_device():
+    """cvs_bands_create validates its arguments before touching CUDA and, without a device, fails loudly (no fallback);
+    cvs_plan_bands (host-only) agrees with the Python planner the gloo tests exercise."""
+    import torch
+
+    from cvsteer_b200 import capi, multi
+    lib = capi.lib()
+    h = C.c_void_p()
+    for args in ((0, 3, 2, 0, 100, 64, 5), (0, 0, 2, 5, 100, 64, 5), (0, 0, 1, 0, 0, 64, 5), (0, 0, 1, 0, 100, 64, 0)):
+        assert lib.cvs_bands_create(C.byref(h), *args, capi.G2_MASK_ORIENT, 4, 0.67) == capi.ERR_INVALID_ARG, args
+    assert lib.cvs_bands_create(C.byref(h), 0, 0, 1, 0, 100, 64, 5, 0, 4, 0.67) == capi.ERR_INVALID_ARG      # empty mask
+    if not torch.cuda.is_available():
+        assert lib.cvs_bands_create(C.byref(h), 0, 0, 1, 0, 100, 64, 5, capi.G2_MASK_ORIENT, 4, 0.67) == capi.ERR_CUDA
+        assert not h.value
+    for rows, world, levels in ((1000, 3, 5), (32768, 8, 5), (77, 4, 3), (16, 8, 5)):
+        plan = (C.c_int * (world * levels * 4))()
+        rpl = (C.c_int * levels)()
+        assert lib.cvs_plan_bands(rows, world, levels, 4, plan, rpl) == 0
+        py = multi.plan_bands(rows, world, levels)
+        for r in range(world):
+            for l in range(levels):
+                q = plan[(r * levels + l) * 4:(r * levels + l) * 4 + 4]
+                assert (q[0], q[1]) == py[r].out[l] and (q[2], q[3]) == py[r].have[l], (rows, world, r, l)
+        assert list(rpl) == py[0].rows

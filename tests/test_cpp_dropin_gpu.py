@@ -65,6 +65,21 @@ def test_cpp_dropin_reference_flow(fish_fixture, tmp_path):
     assert np.array_equal(_load(tmp_path, "strength4", shp), f4.getDominantOrientationStrength())
 
 
+def test_cpp_dropin_eager_mirrors(fish_fixture, tmp_path):
+    """-DCVSTEER_EAGER_HOST_MIRRORS: setup() fills every protected member itself, so subclass code written against the
+    reference (reads m_g2a ... without asking) works with no source change; same outputs as the lazy build."""
+    exe = os.path.join(HERE, "cpp", "test_dropin_eager")
+    assert os.path.exists(exe), "tests/cpp/test_dropin_eager not built (run __graft_entry__.build())"
+    fish = fish_fixture["fish"]
+    src = tmp_path / "fish.u8"
+    fish.tofile(src)
+    r = subprocess.run([exe, str(src), str(fish.shape[0]), str(fish.shape[1]), str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    o = ref.SteerableFiltersG2(fish)
+    rng = basis_range([getattr(o, k) for k in o.PLANES])
+    assert_close_range(_load(tmp_path, "g2a", fish.shape), o.g2a, rng, "eager m_g2a")
+
+
 def test_plain_c_caller_on_gpu():
     exe = os.path.join(HERE, "cpp", "abi_c_check")
     assert os.path.exists(exe), "tests/cpp/abi_c_check not built (run __graft_entry__.build())"
