@@ -473,7 +473,11 @@ def run_cfg5(cx, args):
     ms_c, clk = cx.timed(lambda: run.step("none"), steps, 1)
     res["compute_only_ms"] = round(ms_c, 3)
     res["Mpix_s_compute"] = round(px / 1e6 / (ms_c / 1e3), 1)
-    bpp, ipp = 16 * PYR5 + 5 * (PYR5 - 1) * 4 / 4, 167 * PYR5 + 4 * (PYR5 - 1)
+    # per level-0 pixel: every level reads its input and writes 3 planes (16 B x 1.332); the stand-alone band-mode pyr_down
+    # reads levels 0..3 and writes levels 1..4 once each (4 B x (1.328 + 0.332)); 167 instructions per pixel of every level
+    # + 3.75 per pyr_down input pixel
+    p03 = sum(0.25 ** l for l in range(4))
+    bpp, ipp = 16 * PYR5 + 4 * (p03 + PYR5 - 1), 167 * PYR5 + 3.75 * p03
     res["roofline"] = cx.roofline(px // cx.world, round(bpp, 2), round(ipp, 1), ms_c, "g2_march<M1> + pyr_down per level, band mode")
     res["clocks"] = clk
     if cx.world > 1:
