@@ -86,6 +86,10 @@ NcclApi& nccl()
 // ------------------------------------------------------------------------------------------------
 // the context
 // ------------------------------------------------------------------------------------------------
+// PEER_COPY: a level's output rows are produced in up to kMaxChunks launches so that the copy engine can move chunk k while
+// chunk k+1 computes (matters when few GPUs share the image: at N = 2 a band's level-0 kernel takes 4 ms)
+enum { kMaxChunks = 8, kMinChunkRows = 512 };
+
 struct PlaneRef {
     float* p = nullptr;
     size_t pitch = 0;  // bytes
@@ -111,7 +115,7 @@ struct Bands {
     void* comm = nullptr;             // ncclComm_t
     bool comm_owned = false;
     cudaStream_t xfer = nullptr;      // transfers run here, ordered against the compute stream by events
-    std::vector<cudaEvent_t> ev;      // per level: fused kernel of that level done
+    std::vector<cudaEvent_t> ev;      // per (level, chunk): fused kernel of that chunk done
     cudaEvent_t ev_xfer = nullptr, ev_start = nullptr;
     float* token = nullptr;           // 1 float for the on-stream barrier
 
@@ -195,8 +199,8 @@ extern "C" int cvs_bands_create(cvs_bands** out, int device, int rank, int world
         if (have > 0) e = b->lv[l].reserve(b->pitch[l] * (size_t)have);
     }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->xfer, cudaStreamNonBlocking);
-    b->ev.assign(levels, nullptr);
-    for (int l = 0; l < levels && e == cudaSuccess; ++l) e = cudaEventCreateWithFlags(&b->ev[l], cudaEventDisableTiming);
+    b->ev.assign((size_t)levels * kMaxChunks, nullptr);
+    for (size_t i = 0; i < b->ev.size() && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&b->ev[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_xfer, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_start, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&b->token), 256);
@@ -443,40 +447,53 @@ extern "C" int cvs_bands_run(cvs_bands* b, int gather, void* stream_)
             g.out_row_begin = plan.have[l + 1].first, g.out_row_end = plan.have[l + 1].second, g.out_row_origin = plan.have[l + 1].first;
             CU_TRY(launch_pyr_down(g, static_cast<float*>(b->lv[l + 1].p), s));
         }
-        if (lo < hi) {
+        // chunks of this level's output rows (one chunk unless the copy engine gathers)
+        int nch = 1, chunk_rows = hi - lo;
+        if (xfer && gather == CVS_GATHER_PEER_COPY && hi - lo >= 2 * kMinChunkRows) {
+            chunk_rows = std::max<int>(kMinChunkRows, ((hi - lo + kMaxChunks - 1) / kMaxChunks + 63) / 64 * 64);
+            nch = (hi - lo + chunk_rows - 1) / chunk_rows;
+        }
+        for (int c = 0; c < nch && lo < hi; ++c) {
+            const int clo = lo + c * chunk_rows, chi = std::min(hi, clo + chunk_rows);
             float* outs[CVS_G2_NPLANES] = {nullptr};
             size_t opitch = b->pitch[l];
             for (int k = 0; k < b->nsel; ++k) {
                 if (direct) {
                     const PlaneRef& r = b->rootp[(size_t)l * b->nsel + k];
-                    outs[b->sel[k]] = reinterpret_cast<float*>(reinterpret_cast<char*>(r.p) + (size_t)lo * r.pitch);
+                    outs[b->sel[k]] = reinterpret_cast<float*>(reinterpret_cast<char*>(r.p) + (size_t)clo * r.pitch);
                     opitch = r.pitch;
                 } else {
-                    outs[b->sel[k]] = reinterpret_cast<float*>(static_cast<char*>(b->local.p) + b->local_off[(size_t)l * b->nsel + k]);
+                    outs[b->sel[k]] = reinterpret_cast<float*>(static_cast<char*>(b->local.p) + b->local_off[(size_t)l * b->nsel + k] +
+                                                               (size_t)(clo - lo) * b->pitch[l]);
                 }
             }
             BatchGeom g = whole_frame_geom(b->lv[l].p, false, 1, have_hi - have_lo, b->lc[l], b->pitch[l], 0, opitch, 0);
             g.full_rows = plan.rows[l];
             g.y_origin = have_lo;
-            g.out_row_begin = lo, g.out_row_end = hi, g.out_row_origin = lo;
+            g.out_row_begin = clo, g.out_row_end = chi, g.out_row_origin = clo;
             int rc = run_fused(b->f, g, b->mask, st, outs, s);
             if (rc) return rc;
-        }
-        if (!xfer) continue;
-        // this level's rows travel on the transfer stream while the next level computes on `s`
-        CU_TRY(cudaEventRecord(b->ev[l], s));
-        CU_TRY(cudaStreamWaitEvent(b->xfer, b->ev[l], 0));
-        if (gather == CVS_GATHER_PEER_COPY) {
-            for (int k = 0; k < b->nsel && lo < hi; ++k) {
+            if (!(xfer && gather == CVS_GATHER_PEER_COPY)) continue;
+            // this chunk's rows travel on the transfer stream (copy engine) while the next chunk / level computes on `s`
+            cudaEvent_t ev = b->ev[(size_t)l * kMaxChunks + c];
+            CU_TRY(cudaEventRecord(ev, s));
+            CU_TRY(cudaStreamWaitEvent(b->xfer, ev, 0));
+            for (int k = 0; k < b->nsel; ++k) {
                 const PlaneRef& r = b->rootp[(size_t)l * b->nsel + k];
-                const char* src = static_cast<const char*>(b->local.p) + b->local_off[(size_t)l * b->nsel + k];
-                char* dst = reinterpret_cast<char*>(r.p) + (size_t)lo * r.pitch;
+                const char* src = static_cast<const char*>(b->local.p) + b->local_off[(size_t)l * b->nsel + k] + (size_t)(clo - lo) * b->pitch[l];
+                char* dst = reinterpret_cast<char*>(r.p) + (size_t)clo * r.pitch;
                 if (r.pitch == b->pitch[l])
-                    CU_TRY(cudaMemcpyAsync(dst, src, b->pitch[l] * (size_t)(hi - lo), cudaMemcpyDefault, b->xfer));
+                    CU_TRY(cudaMemcpyAsync(dst, src, b->pitch[l] * (size_t)(chi - clo), cudaMemcpyDefault, b->xfer));
                 else
-                    CU_TRY(cudaMemcpy2DAsync(dst, r.pitch, src, b->pitch[l], (size_t)b->lc[l] * 4, hi - lo, cudaMemcpyDefault, b->xfer));
+                    CU_TRY(cudaMemcpy2DAsync(dst, r.pitch, src, b->pitch[l], (size_t)b->lc[l] * 4, chi - clo, cudaMemcpyDefault, b->xfer));
             }
-        } else {  // NCCL: one group per level; row blocks are contiguous (same pitch on both sides), so no staging copy
+        }
+        if (!xfer || gather == CVS_GATHER_PEER_COPY) continue;
+        // NCCL: this level's rows travel on the transfer stream while the next level computes on `s`
+        CU_TRY(cudaEventRecord(b->ev[(size_t)l * kMaxChunks], s));
+        CU_TRY(cudaStreamWaitEvent(b->xfer, b->ev[(size_t)l * kMaxChunks], 0));
+        {
+            // one group per level; row blocks are contiguous (same pitch on both sides), so no staging copy
             NCCL_TRY(nccl().GroupStart());
             int nerr = 0;
             if (is_root) {

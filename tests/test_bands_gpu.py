@@ -23,10 +23,11 @@ def _whole(img):
     return G2Batch().run_pyramid(torch.from_numpy(img[None]).cuda(), L, capi.G2_MASK_ORIENT)
 
 
-@pytest.mark.parametrize("world,mode", [(1, capi.GATHER_NONE), (3, capi.GATHER_PEER_STORE), (3, capi.GATHER_PEER_COPY), (5, capi.GATHER_PEER_STORE)])
-def test_contexts_of_one_process_equal_whole_image(world, mode):
+@pytest.mark.parametrize("world,mode,H,W", [(1, capi.GATHER_NONE, 1000, 700), (3, capi.GATHER_PEER_STORE, 1000, 700),
+                                            (3, capi.GATHER_PEER_COPY, 1000, 700), (5, capi.GATHER_PEER_STORE, 1000, 700),
+                                            (2, capi.GATHER_PEER_COPY, 2300, 520)])   # 1152-row bands: copied in 3 chunks
+def test_contexts_of_one_process_equal_whole_image(world, mode, H, W):
     """`world` band contexts on ONE device in ONE process: the root exports its block, the others attach the pointer."""
-    H, W = 1000, 700
     img = synth(7100, H, W)
     whole = _whole(img)
     lib = capi.lib()
