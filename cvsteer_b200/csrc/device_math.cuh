@@ -141,40 +141,27 @@ struct Orientation {
 };
 
 // G2.cpp:70-99 on the 7 basis values of one pixel.
-// PRE: the steer-only kernels fold the steering factors into the column taps, so b, hb, hc, hd arrive as -2 b, -3 hb, 3 hc, -hd;
-// the quadratic forms absorb the factors in their constants (all of them stay exact binary fractions):
-//   c1 = .125 B^2 + .25 ac + .375 (aa+cc) + .3125 (haa + HD^2) + .0625 (HB^2 + HC^2) + .125 (ha HC + HB HD)
-//   c2 = .5 (aa-cc) + .46875 (haa - HD^2) + .03125 (HB^2 - HC^2) + .0625 (ha HC - HB HD)
-//   c3 = .5 (a B + B c) + .3125 (HC HD + ha HB) + .1875 HB HC + .1875 ha HD
-template <bool FAST = false, bool PRE = false>
+template <bool FAST = false>
 __device__ __forceinline__ Orientation orientation_g2(float a, float b, float c, float ha, float hb, float hc,
                                                      float hd)
 {
     Orientation o;
     const float aa = a * a, cc = c * c, haa = ha * ha, hdd = hd * hd, hbb = hb * hb, hcc = hc * hc;
     const float hac = ha * hc, hbd = hb * hd;
-    float c1 = (PRE ? 0.125f : 0.5f) * (b * b);
+    float c1 = 0.5f * (b * b);
     c1 = fmaf(0.25f, a * c, c1);
     c1 = fmaf(0.375f, aa + cc, c1);
     c1 = fmaf(0.3125f, haa + hdd, c1);
-    c1 = fmaf(PRE ? 0.0625f : 0.5625f, hbb + hcc, c1);
-    c1 = fmaf(PRE ? 0.125f : 0.375f, hac + hbd, c1);
+    c1 = fmaf(0.5625f, hbb + hcc, c1);
+    c1 = fmaf(0.375f, hac + hbd, c1);
     float c2 = 0.5f * (aa - cc);
     c2 = fmaf(0.46875f, haa - hdd, c2);
-    c2 = fmaf(PRE ? 0.03125f : 0.28125f, hbb - hcc, c2);
-    c2 = fmaf(PRE ? 0.0625f : 0.1875f, hac - hbd, c2);
-    float c3;
-    if (PRE) {
-        c3 = 0.5f * fmaf(a, b, b * c);
-        c3 = fmaf(0.3125f, fmaf(hc, hd, ha * hb), c3);
-        c3 = fmaf(0.1875f, hb * hc, c3);
-        c3 = fmaf(0.1875f, ha * hd, c3);
-    } else {
-        c3 = -(a * b) - b * c;
-        c3 = fmaf(-0.9375f, fmaf(hc, hd, ha * hb), c3);
-        c3 = fmaf(-1.6875f, hb * hc, c3);
-        c3 = fmaf(-0.1875f, ha * hd, c3);
-    }
+    c2 = fmaf(0.28125f, hbb - hcc, c2);
+    c2 = fmaf(0.1875f, hac - hbd, c2);
+    float c3 = -(a * b) - b * c;
+    c3 = fmaf(-0.9375f, fmaf(hc, hd, ha * hb), c3);
+    c3 = fmaf(-1.6875f, hb * hc, c3);
+    c3 = fmaf(-0.1875f, ha * hd, c3);
     o.c1 = c1;
     o.c2 = c2;
     o.c3 = c3;
@@ -191,15 +178,6 @@ __device__ __forceinline__ void steer_g2(float ct, float st, float a, float b, f
     const float ct2 = ct * ct, st2 = st * st, cs = ct * st;
     g2 = fmaf(ct2, a, fmaf(-2.f * cs, b, st2 * c));
     h2 = fmaf(ct2 * ct, ha, fmaf(-3.f * ct2 * st, hb, fmaf(3.f * ct * st2, hc, -(st2 * st) * hd)));
-}
-
-// the same with b, hb, hc, hd pre-multiplied by -2, -3, 3, -1 (steering factors folded into the column taps)
-__device__ __forceinline__ void steer_g2_prescaled(float ct, float st, float a, float b, float c, float ha, float hb, float hc, float hd, float& g2,
-                                                   float& h2)
-{
-    const float ct2 = ct * ct, st2 = st * st, cs = ct * st;
-    g2 = fmaf(ct2, a, fmaf(cs, b, st2 * c));
-    h2 = fmaf(ct2 * ct, ha, fmaf(ct2 * st, hb, fmaf(cs * st, hc, (st2 * st) * hd)));
 }
 
 // G4.cpp:97-111 / :116-121

@@ -23,9 +23,6 @@ namespace cvs {
 #ifndef CVS_G2_MIN_CTAS
 #define CVS_G2_MIN_CTAS 4
 #endif
-#ifndef CVS_G2_PRESCALE
-#define CVS_G2_PRESCALE 1
-#endif
 struct G2Fam {
     static constexpr int R = 4, NSETS = 6, NROW = 5, NBASIS = 7, NPLANES = CVS_G2_NPLANES, BH = CVS_G2_BH, MIN_CTAS = CVS_G2_MIN_CTAS;
     static constexpr bool SHARED_ROW_PASS = CVS_G2_SHARED_ROW;
@@ -51,14 +48,10 @@ struct G2Fam {
     static constexpr int kBakedWidth = CVS_BAKED_G2_WIDTH;
     __host__ __device__ static constexpr float baked(int set, int i) { constexpr float t[NSETS][R + 1] = CVS_BAKED_G2_TAPS; return t[set][i]; }
 
-    // Static kernels with baked taps that steer but output no basis plane fold the steering factors (G2: 1 -2 1, H2: 1 -3 3 -1)
-    // into the column taps at compile time; orientation_g2<.., PRE> absorbs them in its constants.  4 instructions per pixel.
+    // (no steering factors folded into the column taps for this family)
     template <unsigned MASK, bool BAKED>
-    __host__ __device__ static constexpr bool prescaled()
-    {
-        return CVS_G2_PRESCALE && BAKED && MASK != 0 && ((MASK & MARCH_PLANE_BITS) & 0x7Fu) == 0 && ((MASK & MARCH_PLANE_BITS) & kNeedsSteer) != 0;
-    }
-    __host__ __device__ static constexpr float steer_coeff(int q) { constexpr float t[7] = {1.f, -2.f, 1.f, 1.f, -3.f, 3.f, -1.f}; return t[q]; }
+    __host__ __device__ static constexpr bool prescaled() { return false; }
+    __host__ __device__ static constexpr float steer_coeff(int) { return 1.f; }
 
     // does this launch read the per-pixel steering-angle map?
     template <unsigned MASK>
@@ -95,7 +88,7 @@ struct G2Fam {
         const bool need_orient = (m & (CVS_BIT(CVS_C1) | CVS_BIT(CVS_C2) | CVS_BIT(CVS_C3) | CVS_BIT(CVS_THETA) |
                                        CVS_BIT(CVS_STRENGTH) | CVS_BIT(CVS_E))) || src == CVS_STEER_DOMINANT;
         if (need_orient) {
-            o = dev::orientation_g2<FAST, PRESCALED>(b[0], b[1], b[2], b[3], b[4], b[5], b[6]);
+            o = dev::orientation_g2<FAST>(b[0], b[1], b[2], b[3], b[4], b[5], b[6]);
             if (m & CVS_BIT(CVS_C1)) put(CVS_C1, o.c1);
             if (m & CVS_BIT(CVS_C2)) put(CVS_C2, o.c2);
             if (m & CVS_BIT(CVS_C3)) put(CVS_C3, o.c3);
@@ -125,8 +118,7 @@ struct G2Fam {
             if (!(m & kNeedsSteer)) return;
         }
         float g2, h2;
-        if (PRESCALED) dev::steer_g2_prescaled(ct, st, b[0], b[1], b[2], b[3], b[4], b[5], b[6], g2, h2);
-        else dev::steer_g2(ct, st, b[0], b[1], b[2], b[3], b[4], b[5], b[6], g2, h2);
+        dev::steer_g2(ct, st, b[0], b[1], b[2], b[3], b[4], b[5], b[6], g2, h2);
         if (m & CVS_BIT(CVS_G2T)) put(CVS_G2T, g2);
         if (m & CVS_BIT(CVS_H2T)) put(CVS_H2T, h2);
         if (m & (kNeedsSteer & ~(CVS_BIT(CVS_G2T) | CVS_BIT(CVS_H2T)))) {
