@@ -30,8 +30,8 @@
 #ifndef CVS_MARCH_UNROLL_EPILOGUE
 #define CVS_MARCH_UNROLL_EPILOGUE 1
 #endif
-// 1: the slot dispatch of the rolled loop is a balanced compare tree instead of a switch (which nvcc lowers to a
-// constant-memory jump table: LDC + BRX on the critical path of every row).
+// The slot dispatch of the rolled loops is a balanced compare tree, not a switch (which nvcc lowers to a constant-memory
+// jump table: LDC + BRX on the critical path of every row; measured 9-15 % slower).
 // masks with at most this many planes keep a 64-bit base per plane in registers (2 registers each)
 // Two pixels per thread (see k_march's PX): 0 = nowhere, 1 = the M2 kernel (default), 2 = M1 as well.
 // 198 instead of 217 instructions per pixel-row, but with the K-fold unrolled body the loop grows to 57 KB and falls out of
@@ -56,9 +56,6 @@
 #endif
 #ifndef CVS_CURSOR_MAX_PLANES
 #define CVS_CURSOR_MAX_PLANES 8
-#endif
-#ifndef CVS_MARCH_TREE_DISPATCH
-#define CVS_MARCH_TREE_DISPATCH 1
 #endif
 
 namespace cvs {
@@ -774,26 +771,10 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
         if (Fam::template reads_theta_map<MASK>(a) && rt + 1 >= 2 * R && rt + 1 < nrows + 2 * R)
             theta_next = cur.theta(a, rt >= 2 * R ? 1 : 0);
         if constexpr (Fam::SHARED_ROW_PASS) row_pass(rt);
-#if CVS_MARCH_TREE_DISPATCH
         dispatch_tree<0, K>(slot, [&](auto slot_c) {
             if constexpr (!Fam::SHARED_ROW_PASS) row_pass(rt);
             col_pass(rt >= 2 * R, slot_c);
         });
-#else
-        switch (slot) {
-#define CVS_CASE(I)                                                        \
-    case I:                                                                \
-        if constexpr (I < K) {                                             \
-            if constexpr (!Fam::SHARED_ROW_PASS) row_pass(rt);             \
-            col_pass(rt >= 2 * R, std::integral_constant<int, (I < K ? I : 0)>{}); \
-        }                                                                  \
-        break;
-            CVS_CASE(0) CVS_CASE(1) CVS_CASE(2) CVS_CASE(3) CVS_CASE(4) CVS_CASE(5) CVS_CASE(6) CVS_CASE(7) CVS_CASE(8)
-            CVS_CASE(9) CVS_CASE(10) CVS_CASE(11) CVS_CASE(12)
-#undef CVS_CASE
-            default: break;
-        }
-#endif
         slot = (slot + 1 == K) ? 0 : slot + 1;
         if (rt >= 2 * R) emit_row(theta_px);
     }
