@@ -39,7 +39,7 @@ int cvsi::fail(int code, const char* fmt, ...)
 }
 using cvsi::fail;
 
-extern "C" const char* cvs_version(void) { return "cvsteer_b200 0.1.0 (sm_100a)"; }
+extern "C" const char* cvs_version(void) { return "cvsteer_b200 0.2.0 (sm_100a)"; }
 extern "C" const char* cvs_last_error(void) { return g_err; }
 
 extern "C" int cvs_device_count(int* count)

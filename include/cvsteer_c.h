@@ -91,7 +91,12 @@ typedef enum cvs_g4_plane {
 #define CVS_G4_MASK_BASIS 0x000007FFu
 #define CVS_G4_MASK_STEER (CVS_BIT(CVS_G4T) | CVS_BIT(CVS_H4T) | CVS_BIT(CVS_MAG4) | CVS_BIT(CVS_PHASE4))
 
-/* Which angle the fused kernels steer to. */
+/* Which angle the fused kernels steer to.
+ * Performance: every mask NAMED above has a fused, fully specialised kernel for every source it is meaningful with (G2: STATE,
+ * ORIENT, FULL, LINES at theta_d; FULL, LINES, STEER5 at a scalar angle or an angle map; G4: BASIS, STEER at a map, a scalar or
+ * theta_d).  Any other combination of planes runs the run-time-mask kernel: same results, exact cv-compatible math (IEEE
+ * division / sqrt, NaNs propagate into theta_d), about half the speed.  The specialised steer kernels use the SFU
+ * approximations (<= 1e-6 rad / 1e-6 of range; NaN inputs give phase 0 as cv::patchNaNs does, but a finite theta_d). */
 typedef enum cvs_steer_source {
     CVS_STEER_DOMINANT = 0, /* per-pixel theta_d computed in the same kernel (what both reference callers do:
                                example/steer.cpp:87, test/test.cpp:86); for G4 see CVS_G4_THETA. */
@@ -318,7 +323,8 @@ CVS_API int cvs_bands_run(cvs_bands* b, int gather, void* stream);
 CVS_API int cvs_bands_barrier(cvs_bands* b, void* stream);
 /* The same from ONE process over n_devices GPUs (a host thread per GPU, peer access to devices[0]): image in host memory,
  * outputs device-resident in caller-owned planes root_planes[level][plane] on devices[0] (row pitch root_pitches[level]).
- * gather = CVS_GATHER_PEER_STORE or CVS_GATHER_PEER_COPY.  Synchronous. */
+ * gather = CVS_GATHER_PEER_STORE or CVS_GATHER_PEER_COPY.  Synchronous; it runs on the library's own non-blocking streams, so
+ * work the caller still has in flight on the output planes (e.g. a fill) must have completed before the call. */
 CVS_API int cvs_g2_run_bands_dev_multi(int n_devices, const int* devices, int width, float spacing, const float* image, int rows,
                                        int cols, size_t step, int levels, unsigned mask, int gather,
                                        float* const* const* root_planes, const size_t* root_pitches);

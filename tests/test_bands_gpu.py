@@ -97,6 +97,7 @@ def test_run_bands_dev_multi_one_process(mode):
     pitches = (C.c_size_t * L)(*[s[1] * 4 for s in shapes])
     darr = (C.c_int * len(devs))(*devs)
     himg = torch.from_numpy(img)
+    torch.cuda.synchronize()      # the call runs on the library's own (non-blocking) streams: the fills above must have landed
     capi.check(lib.cvs_g2_run_bands_dev_multi(len(devs), darr, 4, 0.67, himg.data_ptr(), H, W, W * 4, L, capi.G2_MASK_ORIENT, mode, lvl, pitches))
     torch.cuda.synchronize()
     for l in range(L):
