@@ -54,6 +54,12 @@
 #ifndef CVS_MARCH_PIPE
 #define CVS_MARCH_PIPE 1
 #endif
+// two-pixel kernels (64 threads): minimum CTAs per SM for the register cap.  6 -> 168 registers (ptxas settles at 155-164 without
+// spills instead of 167-189), so shared memory (5 CTAs) and not the register file (4) bounds the occupancy: 10 warps per SM
+// instead of 8, measured +1.0-1.5 % on M2 and +2.5 % on steer5@scalar.  0 = the family's MIN_CTAS (no cap at 64 threads).
+#ifndef CVS_PX2_MIN_CTAS
+#define CVS_PX2_MIN_CTAS 6
+#endif
 #ifndef CVS_CURSOR_MAX_PLANES
 #define CVS_CURSOR_MAX_PLANES 8
 #endif
@@ -405,7 +411,7 @@ __device__ __forceinline__ void emit_next_level(const float* tile, const MarchAr
 // shared-memory loads (K + 1 values as 8-byte loads feed two pixels instead of K values feeding one), store instructions
 // and their 64-bit address arithmetic (one 8-byte store per plane for two pixels), loop control.
 template <class Fam, unsigned MASK /* 0 = use a.mask at run time */, bool USE_TMA, typename TIn, bool BAKED, int PX = 1>
-__global__ void __launch_bounds__(MARCH_TW / PX, Fam::MIN_CTAS)
+__global__ void __launch_bounds__(MARCH_TW / PX, (PX == 2 && CVS_PX2_MIN_CTAS > 0) ? CVS_PX2_MIN_CTAS : Fam::MIN_CTAS)
 k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchArgs a,
         const __grid_constant__ TapTable<Fam::NSETS, Fam::R> taps)
 {
