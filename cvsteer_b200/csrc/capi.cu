@@ -689,7 +689,12 @@ int run_batch_host(Filter* f, int family, const float* in, int n, int rows, int 
         cp.dstPtr = make_cudaPitchedPtr(din, pitch, (size_t)cols * 4, rows);
         cp.extent = make_cudaExtent((size_t)cols * 4, rows, nf);
         cp.kind = cudaMemcpyHostToDevice;
-        if (in_frame_stride % in_step == 0) {
+        // fully contiguous on both sides (the common case: dense frames whose row is a multiple of 128 bytes): one linear copy,
+        // which the copy engine streams a little faster than the equivalent pitched 3-D copy
+        const bool in_dense = pitch == (size_t)cols * 4 && in_step == pitch && in_frame_stride == fbytes;
+        if (in_dense) {
+            CU_TRY(cudaMemcpyAsync(din, reinterpret_cast<const char*>(in) + (size_t)f0 * in_frame_stride, (size_t)nf * fbytes, cudaMemcpyHostToDevice, s));
+        } else if (in_frame_stride % in_step == 0) {
             CU_TRY(cudaMemcpy3DAsync(&cp, s));
         } else {
             for (int k = 0; k < nf; ++k)
@@ -707,7 +712,9 @@ int run_batch_host(Filter* f, int family, const float* in, int n, int rows, int 
         for (int p = 0; p < NPLANES; ++p)
             if (mask >> p & 1u) {
                 char* dst = reinterpret_cast<char*>(outs[p]) + (size_t)f0 * out_frame_stride;
-                if (out_frame_stride % out_step == 0) {
+                if (pitch == (size_t)cols * 4 && out_step == pitch && out_frame_stride == fbytes) {
+                    CU_TRY(cudaMemcpyAsync(dst, douts[p], (size_t)nf * fbytes, cudaMemcpyDeviceToHost, s));
+                } else if (out_frame_stride % out_step == 0) {
                     cudaMemcpy3DParms cq{};
                     cq.srcPtr = make_cudaPitchedPtr(douts[p], pitch, (size_t)cols * 4, rows);
                     cq.dstPtr = make_cudaPitchedPtr(dst, out_step, (size_t)cols * 4, out_frame_stride / out_step);

@@ -232,6 +232,31 @@ def test_host_batch_api_matches_device_path():
     assert torch.equal(oh2[capi.PHASE], oh[capi.PHASE])
 
 
+def test_host_batch_dense_rows_take_linear_copies_and_match():
+    """Rows that are a multiple of 128 bytes (1920 and 3840 columns are) make frames dense on the device: the pipeline
+    then moves each chunk with ONE linear copy per plane.  Dense input + dense outputs, dense input + strided outputs and
+    strided input + dense outputs must all equal the device launch bit for bit."""
+    n, R, Cc = 5, 96, 256
+    fr = _frames(3901, n, R, Cc)
+    g = G2Batch()
+    dev = g.run(torch.from_numpy(fr).cuda(), capi.G2_MASK_FULL)
+    planes = [p for p in range(capi.G2_NPLANES) if capi.G2_MASK_FULL >> p & 1]
+    dense_in = torch.from_numpy(fr).pin_memory()
+    wide_in = torch.zeros((n, R + 3, Cc + 32), dtype=torch.float32).pin_memory()
+    wide_in[:, :R, :Cc] = dense_in
+    for xin, strided_out in ((dense_in, False), (dense_in, True), (wide_in[:, :R, :Cc], False)):
+        if strided_out:
+            big = {p: torch.full((n, R + 2, Cc + 64), -7.0, dtype=torch.float32).pin_memory() for p in planes}
+            oh = {p: big[p][:, :R, :Cc] for p in planes}
+        else:
+            oh = {p: torch.empty((n, R, Cc), dtype=torch.float32).pin_memory() for p in planes}
+        g.run_host(xin, capi.G2_MASK_FULL, oh)
+        for p in planes:
+            assert torch.equal(oh[p], dev[capi.G2_PLANE_NAMES[p]].cpu()), (capi.G2_PLANE_NAMES[p], strided_out)
+        if strided_out:  # nothing outside the views was touched
+            assert all(float(big[p][:, R:, :].max()) == -7.0 and float(big[p][:, :, Cc:].max()) == -7.0 for p in planes)
+
+
 def test_batch_api_errors():
     import ctypes as C
     g = G2Batch()
