@@ -237,6 +237,15 @@ struct OutCursor {
                      : "l"(th_base), "r"(idx + (unsigned)rows_ahead * pitch_elems));
         return v;
     }
+    // ... of the two adjacent pixels of a two-pixel thread (8-byte aligned: x even, map base and pitch multiples of 8, host-checked)
+    __device__ __forceinline__ float2 theta2(const MarchArgs&, int rows_ahead = 0) const
+    {
+        float2 v;
+        asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %3, 4, %2;\n\tld.global.nc.v2.f32 {%0, %1}, [a];\n\t}"
+                     : "=f"(v.x), "=f"(v.y)
+                     : "l"(th_base), "r"(idx + (unsigned)rows_ahead * pitch_elems));
+        return v;
+    }
     __device__ __forceinline__ void next_row() { idx += pitch_elems; }
 };
 
@@ -262,6 +271,10 @@ struct OutCursor<0u, NPLANES> {  // run-time mask: one shared byte offset, 64-bi
     __device__ __forceinline__ float theta(const MarchArgs& a, int rows_ahead = 0) const
     {
         return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(a.theta_map) + off + rows_ahead * pitch);
+    }
+    __device__ __forceinline__ float2 theta2(const MarchArgs& a, int rows_ahead = 0) const
+    {
+        return *reinterpret_cast<const float2*>(reinterpret_cast<const char*>(a.theta_map) + off + rows_ahead * pitch);
     }
     __device__ __forceinline__ void next_row() { off += pitch; }
 };
@@ -590,12 +603,12 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
     using Cursor = OutCursor<((__builtin_popcount(MASK & MARCH_PLANE_BITS) <= CVS_CURSOR_MAX_PLANES && !Fam::SHARED_ROW_PASS) ? MASK : 0u), Fam::NPLANES>;
     Cursor cur(a, band_off, x);
     // point-wise epilogue of the row just finished by col_pass (+ the stores), then on to the next output row
-    auto emit_row = [&](float th) {
+    auto emit_row = [&](float th, float th_right = 0.f) {  // th_right: the right pixel's steering angle (two-pixel @map kernels)
         if constexpr (PX == 1) {
             Fam::template epilogue<MASK, PRESC, false>(b[0], a, cur, th);
         } else {
             Fam::template epilogue<MASK, PRESC, false>(b[0], a, PairLeft<Cursor>{cur}, th);
-            Fam::template epilogue<MASK, PRESC, false>(b[1], a, PairRight<Cursor>{cur}, th);
+            Fam::template epilogue<MASK, PRESC, false>(b[1], a, PairRight<Cursor>{cur}, th_right);
         }
         cur.next_row();
     };
@@ -647,19 +660,28 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
             ((row_pass(I), push(std::integral_constant<int, I>{})), ...);
         }(std::make_integer_sequence<int, W2>{});
         int rt = W2;
+        // @map kernels: the angle pair of an output row is loaded ONE ROW AHEAD (an L2 hit after the bulk prefetch above), so the
+        // load is in flight during the previous row's arithmetic; the last row of the band re-reads its own angles
+        const bool maps = Fam::template reads_theta_map<MASK>(a);
+        float2 thp = maps ? cur.theta2(a) : make_float2(0.f, 0.f);
+        auto one_row = [&](int tile_row, auto pos_c, auto u_c) {
+            const float2 thn = maps ? cur.theta2(a, tile_row + 1 < total ? 1 : 0) : thp;
+            row_pass(tile_row);
+            push(pos_c);
+            col_lin(u_c);
+            emit_row(thp.x, thp.y);
+            thp = thn;
+        };
 #pragma unroll 1
         for (; rt + U <= total; rt += U) {  // unchecked groups of U output rows: one basic block
             [&]<int... I>(std::integer_sequence<int, I...>) {
-                ((row_pass(rt + I), push(std::integral_constant<int, W2 + I>{}), col_lin(std::integral_constant<int, I>{}), emit_row(0.f)), ...);
+                (one_row(rt + I, std::integral_constant<int, W2 + I>{}, std::integral_constant<int, I>{}), ...);
             }(std::make_integer_sequence<int, U>{});
             shift(std::integral_constant<int, U>{});
         }
 #pragma unroll 1
         for (; rt < total; ++rt) {  // fewer than U rows left (last band of an image): one row per iteration
-            row_pass(rt);
-            push(std::integral_constant<int, W2>{});
-            col_lin(std::integral_constant<int, 0>{});
-            emit_row(0.f);
+            one_row(rt, std::integral_constant<int, W2>{}, std::integral_constant<int, 0>{});
             shift(std::integral_constant<int, 1>{});
         }
         rt_done = total;

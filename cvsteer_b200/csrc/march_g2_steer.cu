@@ -11,7 +11,7 @@ cudaError_t launch_march_g2_steer5(const BatchGeom& g, const MarchArgs& a, const
     if (a.steer_source == CVS_STEER_SCALAR)
         return launch_march_mask<G2Fam, march_key(CVS_G2_MASK_STEER5, CVS_STEER_SCALAR), true, (CVS_MARCH_PX2 > 0)>(g, a, tt, grid, stream, info,
                                                                                                                   "g2_march<steer5@scalar>");
-    return launch_march_mask<G2Fam, march_key(CVS_G2_MASK_STEER5, CVS_STEER_MAP), true>(g, a, tt, grid, stream, info, "g2_march<steer5@map>");
+    return launch_march_mask<G2Fam, march_key(CVS_G2_MASK_STEER5, CVS_STEER_MAP), true, (CVS_MARCH_PX2 > 0)>(g, a, tt, grid, stream, info, "g2_march<steer5@map>");
 }
 
 }  // namespace cvs

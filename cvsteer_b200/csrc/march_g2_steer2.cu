@@ -14,11 +14,12 @@ cudaError_t launch_march_g2_given_angle(const BatchGeom& g, const MarchArgs& a, 
         if (scalar)
             return launch_march_mask<G2Fam, march_key(CVS_G2_MASK_FULL, CVS_STEER_SCALAR), true, (CVS_MARCH_PX2 > 0)>(g, a, tt, grid, stream, info,
                                                                                                                     "g2_march<M2@scalar>");
-        return launch_march_mask<G2Fam, march_key(CVS_G2_MASK_FULL, CVS_STEER_MAP), true>(g, a, tt, grid, stream, info, "g2_march<M2@map>");
+        return launch_march_mask<G2Fam, march_key(CVS_G2_MASK_FULL, CVS_STEER_MAP), true, (CVS_MARCH_PX2 > 0)>(g, a, tt, grid, stream, info, "g2_march<M2@map>");
     }
     if (scalar)
         return launch_march_mask<G2Fam, march_key(CVS_G2_MASK_LINES, CVS_STEER_SCALAR), true, (CVS_MARCH_PX2 > 0)>(g, a, tt, grid, stream, info,
                                                                                                                  "g2_march<lines@scalar>");
+    // (one pixel per thread: measured 152-155 Gpix/s against 142-149 for the two-pixel form of this mask)
     return launch_march_mask<G2Fam, march_key(CVS_G2_MASK_LINES, CVS_STEER_MAP), true>(g, a, tt, grid, stream, info, "g2_march<lines@map>");
 }
 

@@ -132,6 +132,7 @@ static inline bool pair_store_ok(const BatchGeom& g, const MarchArgs& a)
     if (disabled || (g.cols & 1) || (g.out_pitch & 7) || (g.out_frame_stride & 7)) return false;
     for (int p = 0; p < MARCH_MAX_OUT; ++p)
         if (a.out[p] && ((uintptr_t)a.out[p] & 7)) return false;
+    if (a.steer_source == CVS_STEER_MAP && ((uintptr_t)a.theta_map & 7)) return false;  // angle pairs are 8-byte loads as well
     return true;
 }
 

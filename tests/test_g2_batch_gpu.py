@@ -105,6 +105,39 @@ def test_tma_and_ldg_loaders_agree_bitwise():
         assert torch.equal(a[k], b[k]), k
 
 
+@pytest.mark.parametrize("mask_name", ["steer5", "full"])
+def test_two_pixel_map_kernels_match_oracle_and_one_pixel_path(mask_name):
+    """steer(theta map) through the two-pixel static kernels (angle pairs as 8-byte loads, one row ahead): same pixels as the
+    one-pixel kernel that an odd-aligned view falls back to, bit for bit, and within tolerance of the oracle steered at the
+    same angles (reference G2.cpp:167-177).  300 rows: interior bands, a ragged last band and both image borders."""
+    fr = _frames(3310, 2, 300, 392)
+    th = np.random.default_rng(3311).uniform(-4, 4, (2, 300, 392)).astype(np.float32)
+    mask = capi.G2_MASK_STEER5 if mask_name == "steer5" else capi.G2_MASK_FULL
+    g = G2Batch()
+    x, t = torch.from_numpy(fr).cuda(), torch.from_numpy(th).cuda()
+    a = g.run(x, mask, steer=capi.STEER_MAP, theta_map=t)
+    assert g.last_launch()["kernel"].endswith("@map>/tma/imm-taps/2px"), g.last_launch()["kernel"]
+    pad = torch.zeros((2, 300, 395), dtype=torch.float32, device="cuda")
+    pad[:, :, 1:393] = x
+    b = g.run(pad[:, :, 1:393], mask, steer=capi.STEER_MAP, theta_map=t)
+    assert g.last_launch()["kernel"].endswith("/ldg")
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    # an angle map at an address that is not a multiple of 8: the launcher must fall back to one pixel per thread
+    tpad = torch.zeros(2 * 300 * 392 + 1, dtype=torch.float32, device="cuda")
+    tpad[1:] = t.flatten()
+    c = g.run(x, mask, steer=capi.STEER_MAP, theta_map=tpad[1:].view(2, 300, 392))
+    assert g.last_launch()["kernel"].endswith("@map>/tma/imm-taps"), g.last_launch()["kernel"]
+    for k in a:
+        assert torch.equal(a[k], c[k]), k
+    o = ref.SteerableFiltersG2(fr[1])
+    rng = basis_range([getattr(o, k) for k in STATE])
+    w = o.steer_map_full(th[1])
+    for k, j, sc in (("g2", 0, rng), ("h2", 1, rng), ("e", 2, ("own", rng)), ("magnitude", 3, rng)):
+        assert_close_range(a[k][1].cpu().numpy(), w[j], sc, "map/2px " + k)
+    assert_angle_close(a["phase"][1].cpu().numpy(), w[4], w[3], 2 * np.pi, "map/2px phase")
+
+
 def test_u8_input_matches_float_input():
     img8 = np.random.default_rng(4).integers(0, 256, (2, 100, 300), dtype=np.uint8)
     g = G2Batch()

@@ -60,6 +60,8 @@ def main():
         ("g2 lines u8-in", 2, capi.G2_MASK_LINES, "u8", 13, 217),
         ("g2 steer5@scalar", 2, capi.G2_MASK_STEER5, capi.STEER_SCALAR, 24, 117 + 16 + 16 + 50),
         ("g2 steer5@map", 2, capi.G2_MASK_STEER5, capi.STEER_MAP, 28, 117 + 16 + 16 + 60),
+        ("g2 M2@map", 2, capi.G2_MASK_FULL, capi.STEER_MAP, 36, 227),
+        ("g2 lines@map", 2, capi.G2_MASK_LINES, capi.STEER_MAP, 20, 227),
         ("g2 dyn (full+g2a)", 2, dyn_mask, capi.STEER_DOMINANT, 36, 217),
         ("g2 dyn steer5+g2a@map", 2, capi.G2_MASK_STEER5 | capi.bit(capi.G2A), capi.STEER_MAP, 32, 209),
         ("g4 basis", 4, capi.G4_MASK_BASIS, capi.STEER_DOMINANT, 48, 273),
