@@ -124,7 +124,7 @@ def wrap(angle: np.ndarray) -> np.ndarray:
     # `Mat1f > double`: cv::compare converts the scalar to the array depth, so the test is
     # angle > float(M_PI) in float [probe: cv2.compare(float32(pi), math.pi, CMP_GT) == 0].
     m = angle > F32(math.pi)
-    out[m] = tmp[m]
+    np.copyto(out, tmp, where=m)  # wrapped.copyTo(output, mask)
     return out
 
 
@@ -179,7 +179,13 @@ def find_bright_lines(e, phase, k=2.0):  # G2.cpp:209-212
 
 
 def _scale(alpha: float, m: np.ndarray) -> np.ndarray:
-    """MatExpr `double * Mat1f` materialised as float: float(double(alpha)*m)."""
+    """MatExpr `double * Mat1f` materialised as float: float(double(alpha)*m).  Every coefficient of G2.cpp:93-95 has at most
+    5 significant bits, so double(alpha)*m is exact in double and rounds to the same float as the float product: the float32
+    multiply below is bit-identical to the float64 round trip (tests/test_oracle_golden.py checks it) and spares the CPU
+    baseline two conversions per term.  Any other coefficient takes the literal route."""
+    a32 = F32(alpha)
+    if float(a32) == float(alpha) and (np.frexp(float(alpha))[0] * 32.0).is_integer():
+        return a32 * m
     return (alpha * m.astype(np.float64)).astype(F32)
 
 

@@ -134,3 +134,22 @@ def test_pyr_down_definition():
     rows = sum(k[i] * p[:, i:i + 51] for i in range(5))
     full = sum(k[i] * rows[i:i + 37, :] for i in range(5))
     np.testing.assert_allclose(out, full[::2, ::2], atol=1e-4)
+
+
+def test_live_oracle_reproduces_committed_g2_vectors_bitwise(fish_fixture, fish_oracle):
+    """The G2/H2 vectors in tests/golden/fish_oracle_cv2_4_13.npz were written by tests/golden/make_golden.py with the literal
+    float64 `double * Mat1f` round trip and the fancy-index `copyTo`; the oracle now uses a float32 multiply for the dyadic
+    coefficients of G2.cpp:93-95 and np.copyto -- this pins that both are bit-identical to what was committed."""
+    f, (g2, h2, e, mag, phase) = ref.g2_full(fish_fixture["fish"], 4, 0.67)
+    live = dict(c1=f.c1, c2=f.c2, c3=f.c3, theta=f.theta, strength=f.strength, g2=g2, h2=h2, e=e, magnitude=mag, phase=phase)
+    for k in ref.SteerableFiltersG2.PLANES:
+        live[k] = getattr(f, k)
+    for k, v in live.items():
+        assert v.dtype == np.float32 and np.array_equal(v, fish_oracle[k]), k
+    # ... and the coefficient shortcut itself, including values the fish image does not reach
+    m = (np.random.default_rng(5).standard_normal((64, 64)) * 1e4).astype(np.float32)
+    m[0, :6] = [0.0, 1e-45, -1e-45, 3e38, 1e-38, -2e-38]
+    for a in (0.5, 0.25, 0.375, 0.3125, 0.5625, 0.46875, 0.28125, 0.1875, 0.9375, 1.6875, 0.1):
+        with np.errstate(over="ignore"):
+            want = (a * m.astype(np.float64)).astype(np.float32)
+            assert np.array_equal(ref._scale(a, m), want), a
