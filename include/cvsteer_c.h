@@ -210,6 +210,12 @@ typedef struct cvs_batch {
     size_t next_pitch, next_frame_stride;
 } cvs_batch;
 
+/* Layout and speed (results never depend on it): the fast kernels stage tiles by TMA, which needs `in` and in_pitch /
+ * in_frame_stride to be multiples of 16 bytes and the default tap width; the two-pixel kernels (FULL, LINES, STEER5) also need
+ * an even `cols`, output planes / out_pitch / out_frame_stride -- and theta_map for CVS_STEER_MAP -- that are multiples of 8
+ * bytes.  Dense 1920- or 3840-column fp32 frames from cudaMalloc satisfy all of it; anything else silently takes the
+ * one-pixel or the cooperative-loader form of the same kernel (bit-identical planes, 5-40 % slower).  cvs_g2_last_launch
+ * names the kernel that ran. */
 CVS_API int cvs_g2_run_batch_dev(cvs_g2* h, const cvs_batch* b, unsigned mask, int steer_source,
                                  float theta_scalar, const float* theta_map /* device, out_pitch layout */,
                                  float* const* outs, void* stream);
@@ -224,7 +230,9 @@ CVS_API int cvs_pyr_down_dev(int device, const cvs_batch* b, float* out, void* s
 
 /* Host-buffer batch (the end-to-end call a user with frames in host memory makes): uploads in chunks,
  * runs the fused kernel, downloads the selected planes; copies and kernels overlap on internal
- * streams.  Host buffers should be pinned for full PCIe rate.  steer source = dominant. */
+ * streams.  Host buffers should be pinned for full PCIe rate; frames whose rows are dense multiples of 128 bytes (in_step ==
+ * cols * 4 == a multiple of 128, in_frame_stride == rows * in_step, likewise for the outputs) move as one linear copy per
+ * plane and chunk, which reaches the plain-memcpy PCIe rate (bench.py: 0.98 of it).  steer source = dominant. */
 CVS_API int cvs_g2_run_batch_host(cvs_g2* h, const float* in, int n, int rows, int cols, size_t in_step,
                                   size_t in_frame_stride, unsigned mask, float* const* outs,
                                   size_t out_step, size_t out_frame_stride);
