@@ -4,7 +4,7 @@
 # steer-at-angle kernels, the fused min/max statistics and the single-process band contexts.
 set -o pipefail
 mkdir -p gpurun_out
-SEL='tiny or fish or class_vs_oracle or generic or constant or fused_pyramid or band_equals or u8 or lines_u8 or to_u8 or dominant_orientation or fuzz or steer or contexts_of_one_process or dev_multi or sweep'
+SEL='tiny or fish or class_vs_oracle or generic or constant or fused_pyramid or band_equals or u8 or lines_u8 or to_u8 or dominant_orientation or fuzz or steer or contexts_of_one_process or dev_multi or sweep or two_pixel_map or dense_rows'
 for tool in memcheck racecheck synccheck; do
   echo "== $tool"
   compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest tests/test_g2_class_gpu.py tests/test_g4_gpu.py tests/test_g2_batch_gpu.py tests/test_lines_u8_gpu.py tests/test_bands_gpu.py \
