@@ -95,21 +95,36 @@ def _read_pgm(path):
 
 
 def test_cvsteer_run_cli(fish_fixture, tmp_path):
+    """The reference CLI's contract (example/steer.cpp:59-173): a list of image files in, three PNG maps per file out; PNG
+    (gray and colour) and binary PGM inputs, an unreadable file skipped silently; --format=pgm for PGM outputs."""
     assert os.path.exists(CLI), "cvsteer-run not built (run __graft_entry__.build())"
-    imgs = {"fish": fish_fixture["fish"], "noise": np.random.default_rng(1).integers(0, 256, (97, 203), dtype=np.uint8)}
-    for k, v in imgs.items():
-        _write_pgm(tmp_path / f"{k}.pgm", v)
+    rng = np.random.default_rng(1)
+    colour = rng.integers(0, 256, (60, 90, 3), dtype=np.uint8)
+    imgs = {"fish": fish_fixture["fish"], "noise": rng.integers(0, 256, (97, 203), dtype=np.uint8),
+            "colour": cv2.cvtColor(colour, cv2.COLOR_BGR2GRAY)}            # what the reference's imread + cvtColor sees
+    _write_pgm(tmp_path / "fish.pgm", imgs["fish"])
+    assert cv2.imwrite(str(tmp_path / "noise.png"), imgs["noise"]) and cv2.imwrite(str(tmp_path / "colour.png"), colour)
+    (tmp_path / "text.png").write_text("not an image")
     lst = tmp_path / "files.txt"
-    lst.write_text("".join(f"{tmp_path}/{k}.pgm\n" for k in imgs) + f"{tmp_path}/missing.pgm\n")
+    lst.write_text(f"{tmp_path}/fish.pgm\n{tmp_path}/noise.png\n{tmp_path}/colour.png\n{tmp_path}/missing.png\n{tmp_path}/text.png\n")
     out = tmp_path / "out"
     out.mkdir()
     r = subprocess.run([CLI, f"--input={lst}", f"--output={out}", "--verbose"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
-    assert "2 of 3 files processed" in r.stdout            # the unreadable file is skipped silently, like the reference
+    assert "3 of 5 files processed" in r.stdout            # unreadable files are skipped silently, like the reference
     for k, v in imgs.items():
         want = _oracle_maps(v)
         for j, suffix in enumerate(("edges", "lines_dark", "lines_bright")):
-            _assert_u8_close(_read_pgm(out / f"{k}_{suffix}.pgm"), want[j], f"{k}_{suffix}")
+            got = cv2.imread(str(out / f"{k}_{suffix}.png"), cv2.IMREAD_UNCHANGED)   # the reference's output names
+            assert got is not None and got.dtype == np.uint8 and got.shape == v.shape
+            _assert_u8_close(got, want[j], f"{k}_{suffix}")
+    # PGM outputs on request; a single image instead of a list
+    out2 = tmp_path / "out2"
+    out2.mkdir()
+    r = subprocess.run([CLI, f"--input={tmp_path}/noise.png", f"--output={out2}", "--format=pgm"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for suffix in ("edges", "lines_dark", "lines_bright"):
+        assert np.array_equal(_read_pgm(out2 / f"noise_{suffix}.pgm"), cv2.imread(str(out / f"noise_{suffix}.png"), cv2.IMREAD_UNCHANGED))
     assert "Usage" in subprocess.run([CLI, "--help"], capture_output=True, text=True).stdout
 
 
