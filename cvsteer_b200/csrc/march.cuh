@@ -715,6 +715,12 @@ k_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MarchA
             }
         }
     }
+    // What bounds this loop: instruction FETCH.  One row walks the slot-independent code (2.7 KB) and one of 2R slot bodies
+    // (2.3 KB each for G4), 30 KB per window rotation against a per-scheduler L0 instruction cache of a few KB.  Measured
+    // (profiles/experiments/r02_g4_icache_diagnostics.md): with the rows cycling through 1 / 2 / 4 / 12 bodies -- same
+    // instructions, branches and memory traffic -- g4 steer@map runs at 112 / 105 / 94 / 88 Gpix/s.  Shifting the window
+    // (fewer bodies), phase-locking the warps of a scheduler (three strips per CTA) and straight-line groups of 2R rows
+    // were all measured slower; do not expect ALU-side micro-optimisations to show (+-3 instructions per row: no effect).
     constexpr bool PIPE = CVS_MARCH_PIPE && Fam::SHARED_ROW_PASS && MASK != 0 && PX == 1 && !SHIFT;
     if constexpr (PIPE) {
         // 2R-slot window: when the newest row arrives in r[], the rows at offsets -R .. R-1 sit in slots
