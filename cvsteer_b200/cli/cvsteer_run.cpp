@@ -101,7 +101,10 @@ bool decode_pgm(const std::vector<unsigned char>& file, std::vector<unsigned cha
         }
         if (pos >= file.size() || file[pos] < '0' || file[pos] > '9') return false;
         v = 0;
-        while (pos < file.size() && file[pos] >= '0' && file[pos] <= '9') v = v * 10 + (file[pos++] - '0');
+        while (pos < file.size() && file[pos] >= '0' && file[pos] <= '9') {
+            if (v > (1 << 26)) return false;  // (a damaged header: no int overflow, no absurd allocation)
+            v = v * 10 + (file[pos++] - '0');
+        }
         ++pos;  // exactly one whitespace byte follows the number
         return true;
     };

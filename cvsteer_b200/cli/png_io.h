@@ -115,6 +115,9 @@ inline bool decode_gray(const unsigned char* file, size_t size, std::vector<unsi
         const int pw = (w - ps.x0 + ps.dx - 1) / ps.dx, ph = (h - ps.y0 + ps.dy - 1) / ps.dy;
         if (pw > 0 && ph > 0) total += (size_t)ph * (rowbytes_of(pw) + 1);
     }
+    // A deflate stream expands at most ~1032 : 1, so a header that promises more than the IDAT bytes could ever inflate to is
+    // damaged (or hostile): reject it before allocating what it asks for.
+    if (total > idat.size() * 1040 + 64 || (size_t)w * (size_t)h > ((size_t)1 << 33)) return false;
     std::vector<unsigned char> raw(total);
     uLongf got = (uLongf)total;
     if (uncompress(raw.data(), &got, idat.data(), (uLong)idat.size()) != Z_OK || got != total) return false;

@@ -155,6 +155,13 @@ def test_damaged_files_are_rejected(tool, tmp_path):
     assert _decode(tool, bytes(bad_crc), tmp_path, "crc") is None
     assert _decode(tool, good[: len(good) // 2], tmp_path, "cut") is None
     assert _decode(tool, b"P5\n2 2\n255\n\0\0\0\0", tmp_path, "notpng") is None
+    # a header that promises far more pixels than the IDAT bytes could inflate to (found by fuzzing: it used to allocate
+    # tens of GB before looking at the data) is rejected up front
+    huge = bytearray(good)
+    huge[16:24] = struct.pack(">II", 0x40000, 0x40000)
+    ihdr = bytes(huge[12:29])
+    huge[29:33] = struct.pack(">I", zlib.crc32(ihdr) & 0xFFFFFFFF)
+    assert _decode(tool, bytes(huge), tmp_path, "huge") is None
 
 
 def test_encoder_round_trips_through_opencv(tool, tmp_path, fish_fixture):
